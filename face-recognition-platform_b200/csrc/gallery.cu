@@ -1,0 +1,516 @@
+// HBM-resident watchlist gallery.  Replaces state.ENCODINGS (backend/app/state.py:78)
+// and the per-call `np.array([ENCODINGS[t] ...])` rebuild (face_service.py:409).
+//
+// Layout per gallery (row = insertion sequence = tie order):
+//   g16   [cap][dimp] fp16   streaming scan copy (COS: L2-normalised rows)
+//   g32   [cap][dimp] fp32   master for the exact re-rank (COS: normalised)
+//   norm2 [cap]       fp32   |g|^2 of the master row (L2 epilogue term)
+//   alive [cap]       u8     tombstones (del ENCODINGS[t], face_service.py:521-523)
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "frp_device.cuh"
+#include "frp_internal.h"
+
+namespace frp {
+
+static thread_local std::string t_error;
+static thread_local const char* t_match_path = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+void set_match_path(const char* name) { t_match_path = name; }
+
+// One warp per row: fp64 norm, optional normalisation, fp32 master + fp16 copy.
+__global__ void ingest_rows_kernel(const float* __restrict__ src, uint64_t n, int dim, int dimp,
+                                   int metric, uint64_t first_row, __half* __restrict__ g16,
+                                   float* __restrict__ g32, float* __restrict__ norm2,
+                                   uint8_t* __restrict__ alive, float* __restrict__ gmax) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n) return;
+    const float* s = src + w * (uint64_t)dim;
+    double acc = 0.0;
+    for (int i = lane; i < dim; i += 32) {
+        const double x = (double)s[i];
+        acc += x * x;
+    }
+    acc = warp_sum_f64(acc);
+    double scale = 1.0;
+    if (metric == FRP_METRIC_COS) scale = acc > 0.0 ? 1.0 / sqrt(acc) : 0.0;
+    const uint64_t row = first_row + w;
+    double acc2 = 0.0;
+    for (int i = lane; i < dimp; i += 32) {
+        float v = 0.f;
+        if (i < dim) v = (float)((double)s[i] * scale);
+        g32[row * dimp + i] = v;
+        g16[row * dimp + i] = __float2half_rn(v);
+        acc2 += (double)v * (double)v;
+    }
+    acc2 = warp_sum_f64(acc2);
+    if (lane == 0) {
+        norm2[row] = (float)acc2;
+        alive[row] = 1;
+        // monotone upper bound of |g| (rounded up); positive floats order like ints
+        const float nr = __double2float_ru(sqrt(acc2));
+        atomicMax((int*)gmax, __float_as_int(nr));
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src32, const __half* __restrict__ src16,
+                                   const float* __restrict__ srcn, const uint64_t* __restrict__ idx,
+                                   uint64_t n, int dimp, float* __restrict__ dst32,
+                                   __half* __restrict__ dst16, float* __restrict__ dstn,
+                                   uint8_t* __restrict__ dalive) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n) return;
+    const uint64_t r = idx[w];
+    for (int i = lane; i < dimp; i += 32) {
+        dst32[w * dimp + i] = src32[r * dimp + i];
+        dst16[w * dimp + i] = src16[r * dimp + i];
+    }
+    if (lane == 0) {
+        dstn[w] = srcn[r];
+        dalive[w] = 1;
+    }
+}
+
+static int pad_dim(int dim) {
+    int p = 64;
+    while (p < dim) p <<= 1;
+    return p;
+}
+
+static void free_buffers(frp_gallery* g) {
+    if (g->g16) cudaFree(g->g16);
+    if (g->g32) cudaFree(g->g32);
+    if (g->norm2) cudaFree(g->norm2);
+    if (g->alive) cudaFree(g->alive);
+    g->g16 = nullptr; g->g32 = nullptr; g->norm2 = nullptr; g->alive = nullptr;
+}
+
+static int alloc_buffers(int dimp, uint64_t cap, __half** g16, float** g32, float** norm2,
+                         uint8_t** alive) {
+    *g16 = nullptr; *g32 = nullptr; *norm2 = nullptr; *alive = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)g16, cap * dimp * sizeof(__half))) != cudaSuccess ||
+        (e = cudaMalloc((void**)g32, cap * dimp * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)norm2, cap * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc((void**)alive, cap)) != cudaSuccess) {
+        set_error("gallery allocation of %llu rows x %d failed: %s", (unsigned long long)cap, dimp,
+                  cudaGetErrorString(e));
+        if (*g16) cudaFree(*g16);
+        if (*g32) cudaFree(*g32);
+        if (*norm2) cudaFree(*norm2);
+        if (*alive) cudaFree(*alive);
+        cudaGetLastError();
+        return FRP_E_NOMEM;
+    }
+    return FRP_OK;
+}
+
+// caller holds the unique lock
+static int ensure_capacity(frp_gallery* g, uint64_t need) {
+    if (need <= g->capacity) return FRP_OK;
+    uint64_t cap = g->capacity ? g->capacity : 1024;
+    while (cap < need) cap = cap + cap / 2 + 1024;
+    __half* n16; float* n32; float* nn; uint8_t* na;
+    int rc = alloc_buffers(g->dimp, cap, &n16, &n32, &nn, &na);
+    if (rc) return rc;
+    if (g->rows) {
+        FRP_CUDA(cudaMemcpy(n16, g->g16, g->rows * g->dimp * sizeof(__half), cudaMemcpyDeviceToDevice));
+        FRP_CUDA(cudaMemcpy(n32, g->g32, g->rows * g->dimp * sizeof(float), cudaMemcpyDeviceToDevice));
+        FRP_CUDA(cudaMemcpy(nn, g->norm2, g->rows * sizeof(float), cudaMemcpyDeviceToDevice));
+        FRP_CUDA(cudaMemcpy(na, g->alive, g->rows, cudaMemcpyDeviceToDevice));
+    }
+    free_buffers(g);
+    g->g16 = n16; g->g32 = n32; g->norm2 = nn; g->alive = na;
+    g->capacity = cap;
+    return FRP_OK;
+}
+
+// caller holds the unique lock; src is device fp32 [n][dim]
+static int ingest_device(frp_gallery* g, const float* src, uint64_t n, uint64_t first_row,
+                         cudaStream_t st) {
+    if (n == 0) return FRP_OK;
+    const int wpb = 8;
+    const uint64_t blocks = (n + wpb - 1) / wpb;
+    ingest_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, g->dim, g->dimp, g->metric,
+                                                              first_row, g->g16, g->g32, g->norm2,
+                                                              g->alive, g->d_gmax);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+static int refresh_gmax(frp_gallery* g, cudaStream_t st) {
+    FRP_CUDA(cudaMemcpyAsync(&g->gmax, g->d_gmax, sizeof(float), cudaMemcpyDeviceToHost, st));
+    FRP_CUDA(cudaStreamSynchronize(st));
+    return FRP_OK;
+}
+
+static int append_host_f32(frp_gallery* g, const float* rows, uint64_t n, uint64_t* first_row) {
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    DeviceGuard dg(g->device);
+    int rc = ensure_capacity(g, g->rows + n);
+    if (rc) return rc;
+    const uint64_t first = g->rows;
+    const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * g->dim));
+    float* stage = nullptr;
+    if (n) FRP_CUDA(cudaMalloc((void**)&stage, std::min(n, chunk) * g->dim * sizeof(float)));
+    for (uint64_t lo = 0; lo < n; lo += chunk) {
+        const uint64_t m = std::min(chunk, n - lo);
+        cudaError_t e = cudaMemcpy(stage, rows + lo * g->dim, m * g->dim * sizeof(float),
+                                   cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(stage);
+            set_error("H2D copy of gallery rows failed: %s", cudaGetErrorString(e));
+            return FRP_E_CUDA;
+        }
+        rc = ingest_device(g, stage, m, first + lo, 0);
+        if (rc) { cudaFree(stage); return rc; }
+        FRP_CUDA(cudaStreamSynchronize(0));
+    }
+    if (stage) cudaFree(stage);
+    g->rows += n;
+    if (first_row) *first_row = first;
+    return refresh_gmax(g, 0);
+}
+
+}  // namespace frp
+
+using namespace frp;
+
+extern "C" {
+
+int frp_abi_version(void) { return FRP_ABI_VERSION; }
+const char* frp_last_error(void) { return t_error.c_str(); }
+uint64_t frp_kernel_launches(void) { return g_launches.load(); }
+const char* frp_last_match_path(void) { return t_match_path; }
+
+int frp_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return FRP_E_NODEVICE;
+    }
+    return FRP_OK;
+}
+
+int frp_device_info(int device, char* name, size_t name_len, int* sm_count, uint64_t* mem_bytes,
+                    int* cc_major, int* cc_minor) {
+    cudaDeviceProp p;
+    FRP_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name && name_len) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = (uint64_t)p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return FRP_OK;
+}
+
+int frp_gallery_create(int device, int dim, int metric, uint64_t capacity, frp_gallery_t** out) {
+    if (!out || dim <= 0 || dim > 512 || (metric != FRP_METRIC_L2 && metric != FRP_METRIC_COS)) {
+        set_error("frp_gallery_create: invalid argument (dim=%d metric=%d)", dim, metric);
+        return FRP_E_INVALID;
+    }
+    int ndev = 0;
+    int rc = frp_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) {
+        set_error("frp_gallery_create: device %d out of range (%d visible)", device, ndev);
+        return FRP_E_INVALID;
+    }
+    cudaDeviceProp p;
+    FRP_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", device,
+                  p.major, p.minor);
+        return FRP_E_NODEVICE;
+    }
+    DeviceGuard dg(device);
+    frp_gallery* g = new frp_gallery();
+    g->device = device;
+    g->dim = dim;
+    g->dimp = pad_dim(dim);
+    g->metric = metric;
+    g->sm_count = p.multiProcessorCount;
+    if (capacity < 1024) capacity = 1024;
+    rc = alloc_buffers(g->dimp, capacity, &g->g16, &g->g32, &g->norm2, &g->alive);
+    if (rc) { delete g; return rc; }
+    g->capacity = capacity;
+    cudaError_t e = cudaMalloc((void**)&g->d_gmax, sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(g->d_gmax, 0, sizeof(float));
+    if (e != cudaSuccess) {
+        set_error("gallery scalar allocation failed: %s", cudaGetErrorString(e));
+        free_buffers(g);
+        delete g;
+        return FRP_E_CUDA;
+    }
+    *out = g;
+    return FRP_OK;
+}
+
+int frp_gallery_destroy(frp_gallery_t* g) {
+    if (!g) return FRP_OK;
+    {
+        DeviceGuard dg(g->device);
+        cudaDeviceSynchronize();
+        free_buffers(g);
+        if (g->d_gmax) cudaFree(g->d_gmax);
+        if (g->tmap_g16) free(g->tmap_g16);
+    }
+    delete g;
+    return FRP_OK;
+}
+
+int frp_gallery_append_f32(frp_gallery_t* g, const float* rows, uint64_t n, uint64_t* first_row) {
+    if (!g || (!rows && n)) { set_error("frp_gallery_append_f32: null argument"); return FRP_E_INVALID; }
+    return append_host_f32(g, rows, n, first_row);
+}
+
+int frp_gallery_append_f64(frp_gallery_t* g, const double* rows, uint64_t n, uint64_t* first_row) {
+    if (!g || (!rows && n)) { set_error("frp_gallery_append_f64: null argument"); return FRP_E_INVALID; }
+    // the reference keeps Python floats (f64, face_service.py:374); the HBM master is fp32
+    std::vector<float> tmp((size_t)n * g->dim);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (float)rows[i];
+    return append_host_f32(g, tmp.data(), n, first_row);
+}
+
+int frp_gallery_append_device(frp_gallery_t* g, const float* rows_dev, uint64_t n, uint64_t* first_row,
+                              void* stream) {
+    if (!g || (!rows_dev && n)) { set_error("frp_gallery_append_device: null argument"); return FRP_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    DeviceGuard dg(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->rows + n > g->capacity) {
+        FRP_CUDA(cudaStreamSynchronize(st));
+        int rc = ensure_capacity(g, g->rows + n);
+        if (rc) return rc;
+    }
+    const uint64_t first = g->rows;
+    int rc = ingest_device(g, rows_dev, n, first, st);
+    if (rc) return rc;
+    g->rows += n;
+    if (first_row) *first_row = first;
+    return refresh_gmax(g, st);
+}
+
+static int update_row(frp_gallery_t* g, uint64_t row, const float* vec) {
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
+    DeviceGuard dg(g->device);
+    uint8_t a = 0;
+    FRP_CUDA(cudaMemcpy(&a, g->alive + row, 1, cudaMemcpyDeviceToHost));
+    if (!a) { set_error("row %llu is deleted", (unsigned long long)row); return FRP_E_RANGE; }
+    float* stage = nullptr;
+    FRP_CUDA(cudaMalloc((void**)&stage, g->dim * sizeof(float)));
+    cudaError_t e = cudaMemcpy(stage, vec, g->dim * sizeof(float), cudaMemcpyHostToDevice);
+    int rc = FRP_OK;
+    if (e != cudaSuccess) { set_error("H2D failed: %s", cudaGetErrorString(e)); rc = FRP_E_CUDA; }
+    if (!rc) rc = ingest_device(g, stage, 1, row, 0);
+    cudaStreamSynchronize(0);
+    cudaFree(stage);
+    if (rc) return rc;
+    return refresh_gmax(g, 0);
+}
+
+int frp_gallery_update_f32(frp_gallery_t* g, uint64_t row, const float* vec) {
+    if (!g || !vec) { set_error("frp_gallery_update_f32: null argument"); return FRP_E_INVALID; }
+    return update_row(g, row, vec);
+}
+int frp_gallery_update_f64(frp_gallery_t* g, uint64_t row, const double* vec) {
+    if (!g || !vec) { set_error("frp_gallery_update_f64: null argument"); return FRP_E_INVALID; }
+    std::vector<float> tmp(g->dim);
+    for (int i = 0; i < g->dim; ++i) tmp[i] = (float)vec[i];
+    return update_row(g, row, tmp.data());
+}
+
+int frp_gallery_remove(frp_gallery_t* g, uint64_t row) {
+    if (!g) { set_error("frp_gallery_remove: null gallery"); return FRP_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
+    DeviceGuard dg(g->device);
+    uint8_t a = 0;
+    FRP_CUDA(cudaMemcpy(&a, g->alive + row, 1, cudaMemcpyDeviceToHost));
+    if (!a) { set_error("row %llu already deleted", (unsigned long long)row); return FRP_E_RANGE; }
+    FRP_CUDA(cudaMemset(g->alive + row, 0, 1));
+    FRP_CUDA(cudaDeviceSynchronize());
+    g->dead += 1;
+    return FRP_OK;
+}
+
+int frp_gallery_count(const frp_gallery_t* g, uint64_t* rows, uint64_t* live) {
+    if (!g) { set_error("frp_gallery_count: null gallery"); return FRP_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lk(g->mu);
+    if (rows) *rows = g->rows;
+    if (live) *live = g->rows - g->dead;
+    return FRP_OK;
+}
+
+int frp_gallery_info(const frp_gallery_t* g, int* device, int* dim, int* dimp, int* metric,
+                     uint64_t* capacity) {
+    if (!g) { set_error("frp_gallery_info: null gallery"); return FRP_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lk(g->mu);
+    if (device) *device = g->device;
+    if (dim) *dim = g->dim;
+    if (dimp) *dimp = g->dimp;
+    if (metric) *metric = g->metric;
+    if (capacity) *capacity = g->capacity;
+    return FRP_OK;
+}
+
+int frp_gallery_set_base(frp_gallery_t* g, uint64_t base_row) {
+    if (!g) { set_error("frp_gallery_set_base: null gallery"); return FRP_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    g->base_row = base_row;
+    return FRP_OK;
+}
+
+int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, frp_gallery_t** out) {
+    if (!g || !out || (!idx && n)) { set_error("frp_gallery_gather: null argument"); return FRP_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lk(g->mu);
+    for (uint64_t i = 0; i < n; ++i)
+        if (idx[i] >= g->rows) { set_error("gather index %llu out of range", (unsigned long long)idx[i]); return FRP_E_RANGE; }
+    frp_gallery_t* ng = nullptr;
+    int rc = frp_gallery_create(g->device, g->dim, g->metric, n, &ng);
+    if (rc) return rc;
+    DeviceGuard dg(g->device);
+    if (n) {
+        uint64_t* didx = nullptr;
+        FRP_CUDA(cudaMalloc((void**)&didx, n * sizeof(uint64_t)));
+        cudaError_t e = cudaMemcpy(didx, idx, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            const int wpb = 8;
+            gather_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32>>>(
+                g->g32, g->g16, g->norm2, didx, n, g->dimp, ng->g32, ng->g16, ng->norm2, ng->alive);
+            e = cudaGetLastError();
+            count_launch();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        cudaFree(didx);
+        if (e != cudaSuccess) {
+            set_error("gather failed: %s", cudaGetErrorString(e));
+            frp_gallery_destroy(ng);
+            return FRP_E_CUDA;
+        }
+    }
+    ng->rows = n;
+    ng->gmax = g->gmax;
+    cudaMemcpy(ng->d_gmax, &ng->gmax, sizeof(float), cudaMemcpyHostToDevice);
+    *out = ng;
+    return FRP_OK;
+}
+
+int frp_gallery_get_row(const frp_gallery_t* g, uint64_t row, float* out) {
+    if (!g || !out) { set_error("frp_gallery_get_row: null argument"); return FRP_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lk(g->mu);
+    if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
+    DeviceGuard dg(g->device);
+    FRP_CUDA(cudaMemcpy2D(out, g->dim * sizeof(float), g->g32 + row * g->dimp, g->dimp * sizeof(float),
+                          g->dim * sizeof(float), 1, cudaMemcpyDeviceToHost));
+    return FRP_OK;
+}
+
+struct SnapshotHeader {
+    char magic[8];  // "FRPGAL1\0"
+    int32_t dim, dimp, metric, reserved;
+    uint64_t rows, dead, base_row;
+    float gmax;
+    float pad;
+};
+
+int frp_gallery_save(const frp_gallery_t* g, const char* path) {
+    if (!g || !path) { set_error("frp_gallery_save: null argument"); return FRP_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lk(g->mu);
+    DeviceGuard dg(g->device);
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return FRP_E_IO; }
+    SnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "FRPGAL1", 8);
+    h.dim = g->dim; h.dimp = g->dimp; h.metric = g->metric;
+    h.rows = g->rows; h.dead = g->dead; h.base_row = g->base_row; h.gmax = g->gmax;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * g->dimp));
+    std::vector<float> buf((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(g->rows, 1)) * g->dimp);
+    for (uint64_t lo = 0; ok && lo < g->rows; lo += chunk) {
+        const uint64_t m = std::min(chunk, g->rows - lo);
+        if (cudaMemcpy(buf.data(), g->g32 + lo * g->dimp, m * g->dimp * sizeof(float),
+                       cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+        ok = fwrite(buf.data(), sizeof(float), (size_t)m * g->dimp, f) == (size_t)m * g->dimp;
+    }
+    std::vector<uint8_t> al((size_t)g->rows);
+    if (ok && g->rows) {
+        ok = cudaMemcpy(al.data(), g->alive, g->rows, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             fwrite(al.data(), 1, al.size(), f) == al.size();
+    }
+    fclose(f);
+    if (!ok) { set_error("write to %s failed", path); cudaGetLastError(); return FRP_E_IO; }
+    return FRP_OK;
+}
+
+int frp_gallery_load(int device, const char* path, frp_gallery_t** out) {
+    if (!path || !out) { set_error("frp_gallery_load: null argument"); return FRP_E_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return FRP_E_IO; }
+    SnapshotHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "FRPGAL1", 8) != 0) {
+        fclose(f);
+        set_error("%s is not a gallery snapshot", path);
+        return FRP_E_IO;
+    }
+    frp_gallery_t* g = nullptr;
+    int rc = frp_gallery_create(device, h.dim, h.metric, h.rows, &g);
+    if (rc) { fclose(f); return rc; }
+    DeviceGuard dg(device);
+    // rows are stored as the (already normalised) fp32 master padded to dimp;
+    // re-ingest reproduces g16 / norm2 bit-identically (normalising a unit row is
+    // not idempotent in fp32, so the master is uploaded verbatim afterwards).
+    const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * h.dimp));
+    std::vector<float> buf((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(h.rows, 1)) * h.dimp);
+    std::vector<float> packed;
+    bool ok = true;
+    for (uint64_t lo = 0; ok && lo < h.rows; lo += chunk) {
+        const uint64_t m = std::min(chunk, h.rows - lo);
+        ok = fread(buf.data(), sizeof(float), (size_t)m * h.dimp, f) == (size_t)m * h.dimp;
+        if (!ok) break;
+        packed.resize((size_t)m * h.dim);
+        for (uint64_t r = 0; r < m; ++r)
+            memcpy(&packed[(size_t)r * h.dim], &buf[(size_t)r * h.dimp], h.dim * sizeof(float));
+        uint64_t first = 0;
+        rc = frp_gallery_append_f32(g, packed.data(), m, &first);
+        if (rc) { fclose(f); frp_gallery_destroy(g); return rc; }
+        ok = cudaMemcpy(g->g32 + lo * h.dimp, buf.data(), m * h.dimp * sizeof(float),
+                        cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    std::vector<uint8_t> al((size_t)h.rows);
+    if (ok && h.rows) {
+        ok = fread(al.data(), 1, al.size(), f) == al.size() &&
+             cudaMemcpy(g->alive, al.data(), h.rows, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    fclose(f);
+    if (!ok) { set_error("read of %s failed", path); frp_gallery_destroy(g); cudaGetLastError(); return FRP_E_IO; }
+    g->dead = h.dead;
+    g->base_row = h.base_row;
+    *out = g;
+    return FRP_OK;
+}
+
+}  // extern "C"

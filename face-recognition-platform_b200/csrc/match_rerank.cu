@@ -1,0 +1,440 @@
+// Query preparation, exact re-rank + certificate (K6), dense score dump, and the
+// cross-shard top-k merge.
+//
+// Replaces the tail of face_service.compare_faces (face_service.py:411-432):
+// threshold, stable sort by distance, and the routes' `[:top_k]`
+// (routes/face.py:692-693); find_k_nearest's argpartition/argsort
+// (face_service.py:601-603).
+#include <math.h>
+
+#include "frp_device.cuh"
+#include "frp_internal.h"
+
+namespace frp {
+
+namespace {
+
+constexpr int kRCap = 128;          // max survivors re-ranked per query
+constexpr int kRerankThreads = 256;
+
+__device__ __forceinline__ float float_round_down(double x) {
+    return __double2float_rd(x);
+}
+
+// ---------------------------------------------------------------------------
+// prep_queries: one block per query.
+// ---------------------------------------------------------------------------
+__global__ void prep_queries_kernel(const float* __restrict__ q, int dim, int dimp, int metric,
+                                    double tau, int flags, float eps_coeff, float gmax,
+                                    float* __restrict__ qprep, __half* __restrict__ q16,
+                                    QParams* __restrict__ qp) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* src = q + (size_t)b * dim;
+    double acc = 0.0;
+    for (int i = tid; i < dim; i += blockDim.x) {
+        const double x = (double)src[i];
+        acc += x * x;
+    }
+    acc = warp_sum_f64(acc);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        double t = (tid < (blockDim.x >> 5)) ? red[tid] : 0.0;
+        t = warp_sum_f64(t);
+        if (tid == 0) red[0] = t;
+    }
+    __syncthreads();
+    const double n2 = red[0];
+    const double nrm = sqrt(n2);
+    double scale = 1.0;
+    if (metric == FRP_METRIC_COS) scale = n2 > 0.0 ? 1.0 / nrm : 0.0;
+    for (int i = tid; i < dimp; i += blockDim.x) {
+        const float v = (i < dim) ? (float)((double)src[i] * scale) : 0.f;
+        qprep[(size_t)b * dimp + i] = v;
+        if (q16) q16[(size_t)b * dimp + i] = __float2half_rn(v);
+    }
+    if (tid == 0) {
+        QParams p;
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        if (metric == FRP_METRIC_COS) {
+            p.eps = eps_coeff * fmaxf(gmax, 1.f) * 1.000001f;
+            p.s_thresh = tau;
+            p.qnorm2 = 1.0;
+        } else {
+            const float qn = __double2float_ru(nrm);
+            p.eps = 2.f * eps_coeff * gmax * qn + 2.4e-7f * (gmax * gmax + 2.f * gmax * qn) + 1e-12f;
+            p.s_thresh = (tau >= 0.0) ? (n2 - tau * tau) : inf;
+            p.qnorm2 = n2;
+        }
+        if (flags & FRP_MATCH_NO_THRESHOLD) {
+            p.cut0 = __int_as_float(0xff800000);   // -inf
+            p.s_thresh = -inf;
+        } else {
+            p.cut0 = float_round_down(p.s_thresh - (double)p.eps);
+        }
+        qp[b] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rerank: one block per query.
+// ---------------------------------------------------------------------------
+struct RerankArgs {
+    const float* g32;
+    const float* qprep;
+    const QParams* qp;
+    const uint64_t* cand;
+    int nlists, KP, k, dimp, metric, flags, npad;
+    double tau;
+    uint64_t base_row;
+    int64_t* out_idx;
+    float* out_score;
+    int32_t* out_count;
+    int32_t* out_status;
+};
+
+__device__ __forceinline__ bool better(int metric, double va, uint32_t ra, double vb, uint32_t rb) {
+    if (metric == FRP_METRIC_COS) return va > vb || (va == vb && ra < rb);
+    return va < vb || (va == vb && ra < rb);
+}
+
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs a) {
+    extern __shared__ __align__(16) uint64_t keys[];   // [npad]
+    __shared__ int s_cnt, s_m, s_npass;
+    __shared__ unsigned int s_lfull;
+    __shared__ double s_kth;
+    __shared__ double ex_s[kRCap], ex_v[kRCap];
+    __shared__ uint32_t ex_row[kRCap];
+    __shared__ uint8_t ex_pass[kRCap];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const QParams qp = a.qp[b];
+    if (tid == 0) { s_cnt = 0; s_lfull = 0u; s_m = 0; s_npass = 0; s_kth = 0.0; }
+    __syncthreads();
+
+    // 1. compact non-empty candidate keys; track the weakest key of every FULL list
+    const int total = a.nlists * a.KP;
+    const uint64_t* cand = a.cand + (size_t)b * total;
+    for (int i = tid; i < total; i += blockDim.x) {
+        const uint64_t key = cand[i];
+        if (key) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            keys[pos] = key;
+            if ((i % a.KP) == a.KP - 1) atomicMax(&s_lfull, (unsigned int)(key >> 32));
+        }
+    }
+    __syncthreads();
+    const int n = s_cnt;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+
+    // 2. block bitonic sort, descending (score desc, row asc)
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            for (int i = tid; i < (np2 >> 1); i += blockDim.x) {
+                const int lo = ((i / stride) * (stride << 1)) + (i % stride);
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t x = keys[lo], y = keys[hi];
+                if (desc ? (x < y) : (x > y)) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // 3. survivors: everything within 2*eps of the k-th best approximate score
+    const int k = a.k;
+    if (n >= k && n > 0) {
+        const float thr = key_score(keys[k - 1]) - 2.f * qp.eps;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const bool p = key_score(keys[i]) >= thr;
+            const bool pn = (i + 1 < n) ? (key_score(keys[i + 1]) >= thr) : false;
+            if (p && !pn) s_m = i + 1;
+        }
+    } else if (tid == 0) {
+        s_m = n;
+    }
+    __syncthreads();
+    const bool overflow = s_m > kRCap;
+    const int m = overflow ? kRCap : s_m;
+
+    // 4. exact fp64 re-rank from the fp32 master (one warp per survivor)
+    const float4* qv = reinterpret_cast<const float4*>(a.qprep + (size_t)b * a.dimp);
+    const int nvec = a.dimp >> 2;
+    for (int c = warp; c < m; c += (blockDim.x >> 5)) {
+        const uint32_t row = key_row(keys[c]);
+        const float4* gr = reinterpret_cast<const float4*>(a.g32 + (size_t)row * a.dimp);
+        double acc = 0.0;
+        if (a.metric == FRP_METRIC_COS) {
+            for (int i = lane; i < nvec; i += 32) {
+                const float4 g = __ldg(gr + i);
+                const float4 q = __ldg(qv + i);
+                acc += (double)g.x * (double)q.x + (double)g.y * (double)q.y +
+                       (double)g.z * (double)q.z + (double)g.w * (double)q.w;
+            }
+        } else {
+            for (int i = lane; i < nvec; i += 32) {
+                const float4 g = __ldg(gr + i);
+                const float4 q = __ldg(qv + i);
+                const double dx = (double)g.x - (double)q.x, dy = (double)g.y - (double)q.y;
+                const double dz = (double)g.z - (double)q.z, dw = (double)g.w - (double)q.w;
+                acc += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) {
+            ex_row[c] = row;
+            if (a.metric == FRP_METRIC_COS) {
+                ex_v[c] = acc;
+                ex_s[c] = acc;
+            } else {
+                ex_v[c] = sqrt(acc);
+                ex_s[c] = qp.qnorm2 - acc;
+            }
+        }
+    }
+    __syncthreads();
+
+    // 5. exact threshold (inclusive like face_service.py:411 unless STRICT), rank, emit
+    const bool thresholded = !(a.flags & FRP_MATCH_NO_THRESHOLD);
+    const bool strict = (a.flags & FRP_MATCH_STRICT) != 0;
+    if (tid < m) {
+        const double v = ex_v[tid];
+        bool p = true;
+        if (thresholded) {
+            if (a.metric == FRP_METRIC_COS) p = strict ? (v > a.tau) : (v >= a.tau);
+            else p = strict ? (v < a.tau) : (v <= a.tau);
+        }
+        if (!(v == v)) p = false;
+        ex_pass[tid] = p ? 1 : 0;
+        if (p) atomicAdd(&s_npass, 1);
+    }
+    __syncthreads();
+    const int npass = s_npass;
+    if (tid < m && ex_pass[tid]) {
+        int rank = 0;
+        const double v = ex_v[tid];
+        const uint32_t r = ex_row[tid];
+        for (int c = 0; c < m; ++c)
+            if (c != tid && ex_pass[c] && better(a.metric, ex_v[c], ex_row[c], v, r)) ++rank;
+        if (rank < k) {
+            a.out_idx[(size_t)b * k + rank] = (int64_t)(a.base_row + r);
+            a.out_score[(size_t)b * k + rank] = (float)v;
+            if (rank == k - 1) s_kth = ex_s[tid];
+        }
+    }
+    const int cnt = npass < k ? npass : k;
+    for (int i = cnt + tid; i < k; i += blockDim.x) {
+        a.out_idx[(size_t)b * k + i] = -1;
+        a.out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+
+    // 6. certificate: rows outside the candidate lists have s_approx <= Lfull
+    //    (or < cut0), hence s_exact <= Lfull + eps (or < s_thresh).
+    if (tid == 0) {
+        a.out_count[b] = cnt;
+        bool ok = !overflow;
+        const bool lf_valid = s_lfull != 0u;
+        const double bound = (double)f32_from_orderable(s_lfull) + (double)qp.eps;
+        if (lf_valid) {
+            if (npass >= k) ok = ok && (s_kth > bound);
+            else ok = ok && thresholded && (bound < qp.s_thresh);
+        }
+        if (a.out_status) a.out_status[b] = ok ? FRP_STATUS_OK : FRP_STATUS_FALLBACK;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dense scores: one warp per gallery row, fp64 from the fp32 master.
+// ---------------------------------------------------------------------------
+__global__ void scores_kernel(const float* __restrict__ g32, const uint8_t* __restrict__ alive,
+                              const float* __restrict__ qprep, uint64_t rows, int dimp, int B,
+                              int metric, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* gr = reinterpret_cast<const float4*>(g32 + row * dimp);
+    const int nvec = dimp >> 2;
+    const bool live = alive[row] != 0;
+    for (int b = 0; b < B; ++b) {
+        const float4* qv = reinterpret_cast<const float4*>(qprep + (size_t)b * dimp);
+        double acc = 0.0;
+        for (int i = lane; i < nvec; i += 32) {
+            const float4 g = __ldg(gr + i);
+            const float4 q = __ldg(qv + i);
+            if (metric == FRP_METRIC_COS) {
+                acc += (double)g.x * (double)q.x + (double)g.y * (double)q.y +
+                       (double)g.z * (double)q.z + (double)g.w * (double)q.w;
+            } else {
+                const double dx = (double)g.x - (double)q.x, dy = (double)g.y - (double)q.y;
+                const double dz = (double)g.z - (double)q.z, dw = (double)g.w - (double)q.w;
+                acc += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) {
+            double v = (metric == FRP_METRIC_COS) ? acc : sqrt(acc);
+            if (!live) v = __longlong_as_double(0x7ff8000000000000ll);   // NaN marks tombstones
+            out[(size_t)b * rows + row] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cross-shard merge: one block per query over R*k gathered entries.
+// ---------------------------------------------------------------------------
+constexpr int kMergeMax = 1024;
+
+// in_* planes of rank r start at base + r * rank_stride (bytes); status may be null.
+__global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t* __restrict__ in_idx_b,
+                                  const uint8_t* __restrict__ in_score_b,
+                                  const uint8_t* __restrict__ in_count_b,
+                                  const uint8_t* __restrict__ in_status_b, size_t rank_stride,
+                                  int64_t* __restrict__ out_idx, float* __restrict__ out_score,
+                                  int32_t* __restrict__ out_count, int32_t* __restrict__ out_any_status) {
+    __shared__ int64_t s_idx[kMergeMax];
+    __shared__ float s_sc[kMergeMax];
+    __shared__ int s_n;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int total = R * k;
+    for (int e = tid; e < total; e += blockDim.x) {
+        const int r = e / k, j = e % k;
+        const int32_t* cnt = reinterpret_cast<const int32_t*>(in_count_b + (size_t)r * rank_stride);
+        if (j < cnt[b]) {
+            const int64_t* idx = reinterpret_cast<const int64_t*>(in_idx_b + (size_t)r * rank_stride);
+            const float* sc = reinterpret_cast<const float*>(in_score_b + (size_t)r * rank_stride);
+            const int pos = atomicAdd(&s_n, 1);
+            s_idx[pos] = idx[(size_t)b * k + j];
+            s_sc[pos] = sc[(size_t)b * k + j];
+        }
+    }
+    if (in_status_b && out_any_status && tid < R) {
+        const int32_t* stt = reinterpret_cast<const int32_t*>(in_status_b + (size_t)tid * rank_stride);
+        if (stt[b] != 0) atomicOr(out_any_status, 1);
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int e = tid; e < n; e += blockDim.x) {
+        const float v = s_sc[e];
+        const int64_t id = s_idx[e];
+        int rank = 0;
+        for (int c = 0; c < n; ++c) {
+            const float vc = s_sc[c];
+            const int64_t ic = s_idx[c];
+            const bool bt = (metric == FRP_METRIC_COS) ? (vc > v || (vc == v && ic < id))
+                                                       : (vc < v || (vc == v && ic < id));
+            if (bt) ++rank;
+        }
+        if (rank < k) {
+            out_idx[(size_t)b * k + rank] = id;
+            out_score[(size_t)b * k + rank] = v;
+        }
+    }
+    const int cnt = n < k ? n : k;
+    for (int i = cnt + tid; i < k; i += blockDim.x) {
+        out_idx[(size_t)b * k + i] = -1;
+        out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+    }
+    if (tid == 0) out_count[b] = cnt;
+}
+
+}  // namespace
+
+int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
+                        float eps_coeff, float* qprep, __half* q16, QParams* qp, cudaStream_t st) {
+    prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, g->dim, g->dimp, g->metric, tau, flags, eps_coeff,
+                                           g->gmax, qprep, q16, qp);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, cudaStream_t st) {
+    if (g->rows == 0) return FRP_OK;
+    const int wpb = 8;
+    const uint64_t blocks = (g->rows + wpb - 1) / wpb;
+    scores_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(g->g32, g->alive, qprep, g->rows, g->dimp, B,
+                                                         g->metric, out);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+// tau travels separately from QParams so the exact comparison uses the caller's double
+int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, int B, int k, int KP,
+                  int flags, double tau, const uint64_t* cand, int nlists, int64_t* out_idx,
+                  float* out_score, int32_t* out_count, int32_t* out_status, cudaStream_t st) {
+    RerankArgs a;
+    a.g32 = g->g32;
+    a.qprep = qprep;
+    a.qp = qp;
+    a.cand = cand;
+    a.nlists = nlists;
+    a.KP = KP;
+    a.k = k;
+    a.dimp = g->dimp;
+    a.metric = g->metric;
+    a.flags = flags;
+    a.tau = tau;
+    a.base_row = g->base_row;
+    a.out_idx = out_idx;
+    a.out_score = out_score;
+    a.out_count = out_count;
+    a.out_status = out_status;
+    int npad = 1;
+    while (npad < nlists * KP) npad <<= 1;
+    a.npad = npad;
+    const size_t smem = (size_t)npad * sizeof(uint64_t);
+    if (smem > 160 * 1024) {
+        set_error("rerank: %d candidate slots exceed shared memory", nlists * KP);
+        return FRP_E_UNSUPPORTED;
+    }
+    static thread_local size_t configured = 0;
+    if (smem > 40 * 1024 && configured < smem) {
+        FRP_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured = smem;
+    }
+    rerank_kernel<<<B, kRerankThreads, smem, st>>>(a);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+}  // namespace frp
+
+extern "C" {
+
+size_t frp_shard_record_bytes(int B, int k) {
+    size_t n = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
+    return (n + 15) / 16 * 16;
+}
+
+int frp_merge_packed_device(int metric, int R, int B, int k, const void* records, int64_t* out_idx,
+                            float* out_score, int32_t* out_count, int32_t* out_any_status,
+                            void* stream) {
+    using namespace frp;
+    if (R <= 0 || B <= 0 || k <= 0 || R * k > kMergeMax || R > 128 || !records || !out_idx || !out_score ||
+        !out_count) {
+        set_error("frp_merge_packed_device: invalid argument (R=%d B=%d k=%d, R*k <= %d)", R, B, k, kMergeMax);
+        return FRP_E_INVALID;
+    }
+    const size_t rec = frp_shard_record_bytes(B, k);
+    const uint8_t* base = (const uint8_t*)records;
+    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 4, o3 = o2 + (size_t)B * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_any_status) FRP_CUDA(cudaMemsetAsync(out_any_status, 0, sizeof(int32_t), st));
+    merge_topk_kernel<<<B, 128, 0, st>>>(metric, R, B, k, base, base + o1, base + o2, base + o3, rec,
+                                         out_idx, out_score, out_count, out_any_status);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+}  // extern "C"

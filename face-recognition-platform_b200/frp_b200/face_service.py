@@ -1,0 +1,327 @@
+"""Drop-in ``FaceService`` for the recognition hot path.
+
+Mirrors the public surface of the reference's
+``backend/app/services/face_service.py`` for the 1:N path — same method names,
+argument meaning, result dictionaries and never-raise error convention — with
+the arithmetic done by libfrp_b200.so on the HBM-resident ``GalleryDict``:
+
+=====================  =======================================  ==================
+method                 reference                                 native entry point
+=====================  =======================================  ==================
+compare_faces          face_service.py:395-443                   frp_scores
+batch_compare_faces    face_service.py:448-481                   frp_match
+find_k_nearest         face_service.py:590-612                   frp_match (no thr.)
+store_face (dup scan)  face_service.py:344-390 (:352-364)        frp_match (strict)
+delete_face            face_service.py:517-547                   frp_gallery_remove
+cluster_faces          face_service.py:552-585                   frp_scores
+get_all_targets        face_service.py:511-512                   —
+match_topk (new)       routes/face.py:688-693 threshold + top-k  frp_match
+=====================  =======================================  ==================
+
+Encoding (dlib / ONNX backbones), Mongo persistence and backups are out of scope
+(SURVEY.md section 8); ``store_face`` / ``delete_face`` take optional persistence
+callbacks instead.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import threading
+import time
+from collections import deque
+from datetime import datetime
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import (MATCH_NO_THRESHOLD, MATCH_STRICT, METRIC_COS, METRIC_L2, FrpError)
+from .gallery import GalleryDict
+
+logger = logging.getLogger("frp_b200.face_service")
+
+DEFAULT_TOLERANCE = float(os.getenv("FACE_TOLERANCE", "0.6"))   # face_service.py:43
+MAX_NATIVE_K = 64
+
+
+class FaceService:
+    """Service for 1:N face matching against the HBM gallery."""
+
+    def __init__(self, encodings: Optional[GalleryDict] = None, tolerance: float = DEFAULT_TOLERANCE,
+                 raise_errors: Optional[bool] = None,
+                 persist: Optional[Callable[[str, list], bool]] = None,
+                 unpersist: Optional[Callable[[str], bool]] = None):
+        self.encodings = encodings if encodings is not None else GalleryDict(METRIC_L2)
+        self.tolerance = tolerance
+        self.raise_errors = (os.getenv("FRP_RAISE", "0") == "1") if raise_errors is None else raise_errors
+        self._persist = persist
+        self._unpersist = unpersist
+        self._metrics_lock = threading.RLock()
+        self._metrics = {"total_comparisons": 0, "cumulative_comparison_time": 0.0}
+        self._comparison_history = deque(maxlen=5000)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def _cos(self) -> bool:
+        return self.encodings.metric == METRIC_COS
+
+    def _fail(self, what: str, exc: Exception, default):
+        logger.exception("Error in %s: %s", what, exc)
+        if self.raise_errors:
+            raise exc
+        return default
+
+    def _get_confidence_level(self, distance: float) -> str:
+        # face_service.py:486-492
+        if distance < 0.4:
+            return "high"
+        if distance < 0.6:
+            return "medium"
+        return "low"
+
+    def _calibrate_confidence(self, distance: float) -> float:
+        # face_service.py:497-506: logistic in (1 - d) clipped to [0, 1], slope 12, 2 decimals
+        x = min(1.0, max(0.0, 1.0 - distance))
+        return round(float(100.0 / (1.0 + np.exp(-12.0 * (x - 0.5)))), 2)
+
+    def _value_key(self) -> str:
+        return "similarity" if self._cos else "distance"
+
+    def _is_match(self, v: np.ndarray, tol: float) -> np.ndarray:
+        return (v >= tol) if self._cos else (v <= tol)
+
+    def _subset(self, target_names):
+        """(names, rows) to check, in the order the reference builds them (face_service.py:403)."""
+        enc = self.encodings
+        if target_names is None:
+            names = enc.keys()
+        else:
+            names = [t for t in target_names if t in enc]
+        rows = np.array([enc.row_of(t) for t in names], dtype=np.int64)
+        return names, rows
+
+    # ---------------------------------------------------------------- compare
+    def compare_faces(self, test_encoding: np.ndarray, target_names: Optional[List[str]] = None,
+                      return_distances: bool = True) -> List[Dict[str, Any]]:
+        start_time = time.time()
+        try:
+            names, rows = self._subset(target_names)
+            if not names:
+                logger.warning("No targets available for comparison")
+                return []
+            q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
+            all_v = self.encodings.gallery.scores(q)[0]
+            v = all_v[rows]
+            matches = self._is_match(v, self.tolerance)
+            key = self._value_key()
+            results: List[Dict[str, Any]] = []
+            now = datetime.now().isoformat()
+            for i, target in enumerate(names):
+                val = float(v[i])
+                item: Dict[str, Any] = {"target": target, "match": bool(matches[i])}
+                if return_distances:
+                    item[key] = val
+                    if not self._cos:
+                        item["confidence"] = self._get_confidence_level(val)
+                        item["confidence_score"] = self._calibrate_confidence(val)
+                results.append(item)
+                self._comparison_history.append({key: val, "match": bool(matches[i]), "timestamp": now})
+            if return_distances:
+                # stable: ties keep dict insertion order (face_service.py:431)
+                if self._cos:
+                    results.sort(key=lambda x: -x.get(key, -1.0))
+                else:
+                    results.sort(key=lambda x: x.get(key, 1.0))
+            dt = time.time() - start_time
+            with self._metrics_lock:
+                self._metrics["total_comparisons"] += len(names)
+                self._metrics["cumulative_comparison_time"] += dt
+            return results
+        except Exception as e:  # reference convention: never raise (face_service.py:441-443)
+            return self._fail("compare_faces", e, [])
+
+    def batch_compare_faces(self, test_encodings: List[np.ndarray],
+                            target_names: Optional[List[str]] = None) -> List[List[Dict[str, Any]]]:
+        try:
+            names, rows = self._subset(target_names)
+            if not names:
+                return [[] for _ in test_encodings]
+            if len(test_encodings) == 0:
+                return []
+            Q = np.stack([np.asarray(t, dtype=np.float32).reshape(-1) for t in test_encodings])
+            key = self._value_key()
+            out: List[List[Dict[str, Any]]] = []
+            if target_names is None:
+                g = self.encodings.gallery
+                idx, sc, cnt, _ = g.match(Q, self.tolerance, MAX_NATIVE_K)
+                dense = None
+                for b in range(len(Q)):
+                    if cnt[b] >= MAX_NATIVE_K:      # possibly more matches than the native k cap
+                        if dense is None:
+                            dense = g.scores(Q)
+                        out.append(self._matches_from_dense(dense[b], names, rows))
+                        continue
+                    res = []
+                    for j in range(int(cnt[b])):
+                        val = float(sc[b, j])
+                        item = {"target": self.encodings.name_of(int(idx[b, j])), "match": True, key: val}
+                        if not self._cos:
+                            item["confidence"] = self._get_confidence_level(val)
+                        res.append(item)
+                    out.append(res)
+            else:
+                dense = self.encodings.gallery.scores(Q)
+                for b in range(len(Q)):
+                    out.append(self._matches_from_dense(dense[b], names, rows))
+            return out
+        except Exception as e:
+            return self._fail("batch_compare_faces", e, [[] for _ in test_encodings])
+
+    def _matches_from_dense(self, all_v, names, rows):
+        key = self._value_key()
+        v = all_v[rows]
+        m = self._is_match(v, self.tolerance)
+        res = []
+        for i in np.nonzero(m)[0]:
+            val = float(v[i])
+            item = {"target": names[int(i)], "match": True, key: val}
+            if not self._cos:
+                item["confidence"] = self._get_confidence_level(val)
+            res.append(item)
+        res.sort(key=(lambda x: -x[key]) if self._cos else (lambda x: x[key]))
+        return res
+
+    def find_k_nearest(self, test_encoding: np.ndarray, k: int = 5) -> List[Dict[str, Any]]:
+        try:
+            if len(self.encodings) == 0:
+                return []
+            k = min(int(k), len(self.encodings))
+            q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
+            key = self._value_key()
+            g = self.encodings.gallery
+            if k <= MAX_NATIVE_K:
+                idx, sc, cnt, _ = g.match(q, 0.0, k, MATCH_NO_THRESHOLD)
+                pairs = [(int(idx[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
+            else:
+                v = g.scores(q)[0]
+                rows = self.encodings.live_rows()
+                order = np.argsort(-v[rows] if self._cos else v[rows], kind="stable")[:k]
+                pairs = [(int(rows[i]), float(v[rows[i]])) for i in order]
+            results = []
+            for row, val in pairs:
+                item = {"target": self.encodings.name_of(row), key: val}
+                if not self._cos:
+                    item["confidence"] = self._get_confidence_level(val)
+                    item["confidence_score"] = self._calibrate_confidence(val)
+                results.append(item)
+            return results
+        except Exception as e:
+            return self._fail("find_k_nearest", e, [])
+
+    def match_topk(self, queries, threshold: Optional[float] = None, top_k: int = 5,
+                   thresholded: bool = True):
+        """Threshold-then-top-k for a batch of queries (the `/face/compare` and
+        `/face/similar` post-processing, routes/face.py:685-693, :800-809) without
+        materialising N dicts.  Returns one list of (target, value) per query."""
+        tol = self.tolerance if threshold is None else threshold
+        Q = np.atleast_2d(np.asarray(queries, dtype=np.float32))
+        if len(self.encodings) == 0:
+            return [[] for _ in Q]
+        flags = 0 if thresholded else MATCH_NO_THRESHOLD
+        idx, sc, cnt, _ = self.encodings.gallery.match(Q, tol, min(int(top_k), MAX_NATIVE_K), flags)
+        return [[(self.encodings.name_of(int(idx[b, j])), float(sc[b, j])) for j in range(int(cnt[b]))]
+                for b in range(len(Q))]
+
+    # ------------------------------------------------------------------ mutate
+    def get_all_targets(self) -> List[str]:
+        return self.encodings.keys()
+
+    def store_face(self, target_name: str, encoding: np.ndarray) -> Dict[str, Any]:
+        try:
+            encoding_list = encoding.tolist() if isinstance(encoding, np.ndarray) else encoding
+            is_duplicate, similar_target = False, None
+            enc = self.encodings
+            if len(enc) and not self._cos:
+                # first existing face (dict order) closer than 0.3, self excluded (face_service.py:352-364)
+                q = np.asarray(encoding_list, dtype=np.float32).reshape(1, -1)
+                idx, sc, cnt, _ = enc.gallery.match(q, 0.3, MAX_NATIVE_K, MATCH_STRICT)
+                if cnt[0] >= MAX_NATIVE_K:
+                    v = enc.gallery.scores(q)[0]
+                    cand = [r for r in enc.live_rows() if v[r] < 0.3]
+                else:
+                    cand = sorted(int(i) for i in idx[0, :cnt[0]])
+                for r in cand:
+                    name = enc.name_of(int(r))
+                    if name is not None and name != target_name:
+                        is_duplicate, similar_target = True, name
+                        logger.warning("Potential duplicate: %s ~ %s", target_name, name)
+                        break
+            already_exists = target_name in enc
+            if self._persist is not None and not self._persist(target_name, encoding_list):
+                return {"success": False, "message": "Failed to store in database", "is_duplicate": is_duplicate}
+            enc[target_name] = encoding_list
+            message = "Face %s successfully for '%s'" % ("updated" if already_exists else "stored", target_name)
+            if is_duplicate:
+                message += " (Warning: Similar to '%s')" % similar_target
+            return {"success": True, "message": message, "is_duplicate": is_duplicate,
+                    "similar_to": similar_target if is_duplicate else None, "was_update": already_exists}
+        except Exception as e:
+            if self.raise_errors:
+                raise
+            logger.exception("Error storing face %s: %s", target_name, e)
+            return {"success": False, "message": "Error storing face: %s" % e, "is_duplicate": False}
+
+    def delete_face(self, target_name: str) -> Dict[str, Any]:
+        try:
+            removed_from_memory = False
+            if target_name in self.encodings:
+                del self.encodings[target_name]
+                removed_from_memory = True
+            removed_from_db = bool(self._unpersist(target_name)) if self._unpersist else False
+            if removed_from_memory or removed_from_db:
+                return {"success": True, "message": "Face '%s' deleted successfully" % target_name,
+                        "removed_from_memory": removed_from_memory, "removed_from_db": removed_from_db}
+            return {"success": False, "message": "Face '%s' not found in database or memory" % target_name}
+        except Exception as e:
+            if self.raise_errors:
+                raise
+            logger.exception("Error deleting face %s: %s", target_name, e)
+            return {"success": False, "message": "Error deleting face: %s" % e}
+
+    def cluster_faces(self, distance_threshold: float = 0.6) -> Dict[str, List[str]]:
+        """Greedy seed clustering of face_service.py:552-585: every not-yet-assigned
+        face (dict order) seeds a cluster and absorbs all unassigned faces within
+        the threshold (inclusive)."""
+        enc = self.encodings
+        if len(enc) < 2:
+            return {"cluster_0": enc.keys()}
+        names = enc.keys()
+        rows = np.array([enc.row_of(t) for t in names], dtype=np.int64)
+        assigned = np.zeros(len(names), bool)
+        clusters: Dict[str, List[str]] = {}
+        cid = 0
+        g = enc.gallery
+        for i, target in enumerate(names):
+            if assigned[i]:
+                continue
+            assigned[i] = True
+            seed = g.get_row(int(rows[i]))[None, :]
+            v = g.scores(seed)[0][rows]
+            close = self._is_match(v, distance_threshold) & ~assigned
+            close[i] = False
+            members = [target] + [names[j] for j in np.nonzero(close)[0]]
+            assigned |= close
+            clusters["cluster_%d" % cid] = members
+            cid += 1
+        return clusters
+
+    # ----------------------------------------------------------------- metrics
+    def get_performance_metrics(self) -> Dict[str, Any]:
+        with self._metrics_lock:
+            m = dict(self._metrics)
+        total = m["total_comparisons"]
+        avg = (m["cumulative_comparison_time"] / total) if total > 0 else 0.0
+        return {**m, "average_comparison_time": round(avg, 4), "total_faces_stored": len(self.encodings),
+                "comparison_history_size": len(self._comparison_history),
+                "kernel_launches": _capi.kernel_launches()}

@@ -1,0 +1,166 @@
+/*
+ * frp_b200.h — C ABI of the B200-native recognition hot path (align + 1:N match).
+ *
+ * The reference (achiever04/face-recognition-platform) is a pure-Python service
+ * with no FFI; the seam this library sits behind is the Python singleton
+ * `face_service` (backend/app/services/face_service.py:769) and the gallery dict
+ * `ENCODINGS` (backend/app/state.py:78).  Each entry point below names the
+ * reference code it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (FRP_OK) or a negative FRP_E_* code; the message
+ *     of the last error of the calling thread is frp_last_error().
+ *   - "_device" variants take device pointers and a cudaStream_t (passed as
+ *     void*; NULL = the legacy default stream) and are asynchronous.
+ *   - host variants copy host<->device inside the call and return synchronised.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with FRP_E_CUDA / FRP_E_NODEVICE.
+ *   - scores: metric L2 -> Euclidean distance (smaller is better, match iff
+ *     d <= tau, face_service.py:410-411); metric COS -> cosine similarity
+ *     (larger is better, match iff s >= tau; insightface compute_sim).
+ *   - ties are broken by gallery row (= dict insertion order; the reference's
+ *     sort is stable over dict order, face_service.py:431).
+ */
+#ifndef FRP_B200_H
+#define FRP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRP_ABI_VERSION 1
+
+/* error codes */
+#define FRP_OK            0
+#define FRP_E_INVALID    -1   /* bad argument */
+#define FRP_E_CUDA       -2   /* CUDA runtime error (see frp_last_error) */
+#define FRP_E_NODEVICE   -3   /* no sm_100 device visible */
+#define FRP_E_NOMEM      -4
+#define FRP_E_IO         -5
+#define FRP_E_UNSUPPORTED -6
+#define FRP_E_RANGE      -7   /* row index out of range / dead row */
+
+/* metrics */
+#define FRP_METRIC_L2   0   /* face_recognition.face_distance, face_service.py:410,597 */
+#define FRP_METRIC_COS  1   /* insightface ArcFaceONNX.compute_sim (third-party) */
+
+/* frp_match flags */
+#define FRP_MATCH_THRESHOLD   0x0  /* threshold then top-k (routes/face.py:692-693) */
+#define FRP_MATCH_NO_THRESHOLD 0x1 /* pure top-k (face_service.py:590-612 find_k_nearest) */
+#define FRP_MATCH_FORCE_SCAN  0x2  /* use the streaming scan kernel for every batch size */
+#define FRP_MATCH_FORCE_GEMM  0x4  /* use the tcgen05 kernel for every batch size */
+#define FRP_MATCH_FORCE_EXACT 0x8  /* scan the fp32 master instead of the fp16 copy */
+#define FRP_MATCH_STRICT      0x10 /* strict comparison (d < tau): store_face duplicate check, face_service.py:360 */
+
+/* per-query status written by frp_match */
+#define FRP_STATUS_OK        0  /* result certified exact w.r.t. the fp32 master */
+#define FRP_STATUS_FALLBACK  1  /* fp16 prefilter could not be certified; result came from the fp32 scan */
+
+typedef struct frp_gallery frp_gallery_t;   /* opaque; replaces state.ENCODINGS (state.py:78) */
+
+/* ---- library / device -------------------------------------------------- */
+int         frp_abi_version(void);
+const char* frp_last_error(void);
+/* number of visible CUDA devices; 0 and FRP_E_NODEVICE when there is none */
+int         frp_device_count(int* count);
+/* name, SM count, global memory bytes and compute capability of `device` */
+int         frp_device_info(int device, char* name, size_t name_len, int* sm_count,
+                            uint64_t* mem_bytes, int* cc_major, int* cc_minor);
+
+/* ---- gallery store: replaces ENCODINGS (state.py:78), the per-call
+ *      np.array([...]) rebuild (face_service.py:409) and store/delete
+ *      (face_service.py:374, :521-523) ---------------------------------------- */
+/* dim: embedding length (128 / 512 / ...); capacity: initial row capacity
+ * (grows on demand).  HBM layout: fp16 scan copy [cap][dimp], fp32 master
+ * [cap][dimp], |g|^2 f32 [cap], alive u8 [cap]; COS rows are L2-normalised on
+ * ingest.  dimp = dim rounded up to a power of two >= 64. */
+int frp_gallery_create(int device, int dim, int metric, uint64_t capacity, frp_gallery_t** out);
+int frp_gallery_destroy(frp_gallery_t* g);
+/* append n rows (host, row-major [n][dim]); *first_row receives the row index
+ * of the first appended row.  Row index == insertion sequence == tie order. */
+int frp_gallery_append_f32(frp_gallery_t* g, const float* rows, uint64_t n, uint64_t* first_row);
+int frp_gallery_append_f64(frp_gallery_t* g, const double* rows, uint64_t n, uint64_t* first_row);
+/* same, rows already in device memory (fp32, row-major [n][dim]) */
+int frp_gallery_append_device(frp_gallery_t* g, const float* rows_dev, uint64_t n,
+                              uint64_t* first_row, void* stream);
+/* overwrite a live row in place (dict assignment to an existing key keeps its
+ * position, face_service.py:374) */
+int frp_gallery_update_f32(frp_gallery_t* g, uint64_t row, const float* vec);
+int frp_gallery_update_f64(frp_gallery_t* g, uint64_t row, const double* vec);
+/* tombstone a row (del ENCODINGS[t], face_service.py:521-523) */
+int frp_gallery_remove(frp_gallery_t* g, uint64_t row);
+/* rows = appended rows incl. tombstones; live = rows - tombstones */
+int frp_gallery_count(const frp_gallery_t* g, uint64_t* rows, uint64_t* live);
+int frp_gallery_info(const frp_gallery_t* g, int* device, int* dim, int* dimp, int* metric,
+                     uint64_t* capacity);
+/* new gallery holding rows idx[0..n) of g in that order (duplicates allowed):
+ * compaction after deletes, and the target_names subset of face_service.py:403 */
+int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, frp_gallery_t** out);
+/* read back the fp32 master row (COS: normalised) */
+int frp_gallery_get_row(const frp_gallery_t* g, uint64_t row, float* out);
+/* flat binary snapshot: header + fp32 master rows + alive flags */
+int frp_gallery_save(const frp_gallery_t* g, const char* path);
+int frp_gallery_load(int device, const char* path, frp_gallery_t** out);
+/* global row index of local row 0 (row-sharded galleries); added to out_idx */
+int frp_gallery_set_base(frp_gallery_t* g, uint64_t base_row);
+
+/* ---- 1:N match: replaces face_distance + `<= tolerance` + sort + [:top_k]
+ *      (face_service.py:410-411,431-432; routes/face.py:692-693) and the
+ *      argpartition top-k of find_k_nearest (face_service.py:601-603) ------- */
+/* queries [B][dim] fp32 host.  Outputs (host): out_idx [B][k] (global row, -1
+ * pad), out_score [B][k] (distance or similarity, NaN pad), out_count [B]
+ * (results per query <= k), out_status [B] (FRP_STATUS_*; may be NULL). */
+int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, int flags,
+              int64_t* out_idx, float* out_score, int32_t* out_count, int32_t* out_status);
+/* same with device buffers; asynchronous on `stream`.  Queries are uncertified
+ * here: out_status must be checked by the caller (FRP_STATUS_FALLBACK rows must
+ * be re-run through frp_match_device with FRP_MATCH_FORCE_EXACT). */
+int frp_match_device(frp_gallery_t* g, const float* queries_dev, int B, double tau, int k,
+                     int flags, int64_t* out_idx_dev, float* out_score_dev,
+                     int32_t* out_count_dev, int32_t* out_status_dev, void* stream);
+/* all N scores of every query from the fp32 master in float64 (the O(N) dict
+ * list compare_faces returns, face_service.py:414-429).  out [B][rows] host. */
+int frp_scores(frp_gallery_t* g, const float* queries, int B, double* out);
+int frp_scores_device(frp_gallery_t* g, const float* queries_dev, int B, double* out_dev, void* stream);
+/* Row-sharded galleries (one rank per GPU): every rank packs its
+ * frp_match_device outputs into one record
+ *     idx[B][k] i64 | score[B][k] f32 | count[B] i32 | status[B] i32   (padded to 16 B)
+ * of frp_shard_record_bytes(B,k) bytes; ncclAllGather concatenates the R records;
+ * frp_merge_packed_device merges them into the global top-k [B][k] (better score
+ * first, ties by global row) and ORs the per-shard status words into
+ * *out_any_status (may be NULL). */
+size_t frp_shard_record_bytes(int B, int k);
+int frp_merge_packed_device(int metric, int R, int B, int k, const void* records_dev,
+                            int64_t* out_idx, float* out_score, int32_t* out_count,
+                            int32_t* out_any_status, void* stream);
+
+/* ---- alignment: insightface face_align.norm_crop + blobFromImages
+ *      (third-party; only call site backend/app/utils/deepfake_utils.py:138) -- */
+/* 2x3 forward similarity matrices from 5 landmarks (skimage _umeyama onto
+ * arcface_dst, float64).  lmk [n][5][2] fp32 host -> M [n][6] f64 host. */
+int frp_estimate_norm(const float* lmk, int n, double* M_out);
+/* frames: F BGR u8 images [F][H][stride] (stride >= 3*W bytes, host);
+ * frame_idx [n]; lmk [n][5][2] fp32 (or NULL when M [n][6] f64 is given).
+ * out_blob [n][3][112][112] fp16 (RGB planes, (v-127.5)/127.5);
+ * out_aligned [n][112][112][3] u8 BGR (optional, may be NULL). */
+int frp_align(int device, const uint8_t* frames, int F, int H, int W, size_t stride,
+              const int32_t* frame_idx, const float* lmk, const double* M, int n,
+              uint16_t* out_blob, uint8_t* out_aligned);
+int frp_align_device(int device, const uint8_t* frames_dev, int F, int H, int W, size_t stride,
+                     const int32_t* frame_idx_dev, const float* lmk_dev, const double* M_dev,
+                     int n, uint16_t* out_blob_dev, uint8_t* out_aligned_dev, void* stream);
+
+/* ---- instrumentation ----------------------------------------------------- */
+/* kernels launched by this library since load (all threads) */
+uint64_t frp_kernel_launches(void);
+/* name of the kernel family the last frp_match* call of this thread used:
+ * "scan_f16", "scan_f32", "gemm_tcgen05" */
+const char* frp_last_match_path(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRP_B200_H */

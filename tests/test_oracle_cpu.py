@@ -1,0 +1,131 @@
+"""The oracle against the golden vectors (reference outputs / installed OpenCV)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import frp_oracle_c as oc
+import frp_oracle_np as o
+import ref_loader
+
+LVL = {"high": 0, "medium": 1, "low": 2}
+
+
+def _enc(G):
+    return {"id%07d" % i: g.tolist() for i, g in enumerate(G)}
+
+
+def test_np_compare_faces_matches_reference_golden(golden_l2):
+    g = golden_l2
+    enc = _enc(g["G"])
+    names = list(enc.keys())
+    for b in range(0, len(g["Q"]), 3):
+        res = o.compare_faces(enc, g["Q"][b], 0.6)
+        assert [names.index(r["target"]) for r in res] == g["order"][b].tolist()
+        assert np.array_equal(np.array([r["distance"] for r in res]), g["dist"][b])      # bit-exact
+        assert np.array_equal(np.array([r["match"] for r in res]), g["match"][b])
+        assert np.array_equal(np.array([r["confidence_score"] for r in res]), g["score"][b])
+        assert [LVL[r["confidence"]] for r in res] == g["conf"][b].tolist()
+
+
+def test_np_topk_and_batch_match_reference_golden(golden_l2):
+    g = golden_l2
+    idx, dist, cnt = o.l2_match_topk(g["G"], g["Q"], 0.6, 5, True)
+    for b in range(len(g["Q"])):
+        want = g["order"][b][g["match"][b]][:5]
+        assert idx[b, :cnt[b]].tolist() == want.tolist()
+    enc = _enc(g["G"])
+    names = list(enc.keys())
+    bat = o.batch_compare_faces(enc, list(g["Q"]), 0.6)
+    for b, r in enumerate(bat):
+        assert len(r) == g["bat_cnt"][b]
+        assert [names.index(x["target"]) for x in r] == g["bat_rows"][b, :len(r)].tolist()
+    # find_k_nearest: pure top-k; argpartition leaves tie order unspecified, so compare distances
+    idx, dist, cnt = o.l2_match_topk(g["G"], g["Q"], 0.0, 5, False)
+    assert np.allclose(dist, g["knn_d"], rtol=0, atol=0)
+
+
+def test_np_subset_semantics(golden_l2):
+    g = golden_l2
+    enc = _enc(g["G"])
+    names = list(enc.keys())
+    sub = [names[r] if r >= 0 else "nope" for r in g["sub_query_rows"]]
+    res = o.compare_faces(enc, g["Q"][0], 0.6, sub)
+    assert [names.index(r["target"]) for r in res] == g["sub_rows"].tolist()
+    assert np.array_equal(np.array([r["distance"] for r in res]), g["sub_dist"])
+
+
+def test_c_oracle_l2_matches_reference_golden(golden_l2):
+    g = golden_l2
+    for b in range(len(g["Q"])):
+        d = oc.l2_distances(g["G"], g["Q"][b])
+        # sqrt(sum of squares) in a different summation order than numpy's pairwise sum
+        assert np.allclose(np.sort(d), g["dist"][b], rtol=0, atol=1e-14)
+        idx, val, n = oc.topk(d, 0, 1, 0.6, 5)
+        want = g["order"][b][g["match"][b]][:5]
+        # exact ties / threshold hits at the 1e-16 level may legitimately differ; they do not
+        # occur away from the planted 0.6 +- 0 rows
+        near = np.abs(g["dist"][b][g["match"][b]][:5] - 0.6) < 1e-12
+        if not near.any():
+            assert idx[:n].tolist() == want.tolist()
+
+
+def test_c_oracle_cos_matches_np(golden_cos):
+    g = golden_cos
+    for b in range(len(g["Q"])):
+        s = oc.cos_scores(g["G"], g["Q"][b])
+        assert np.allclose(s, g["all_scores"][b], rtol=0, atol=1e-12)
+    idx, sc, cnt = o.cos_match_topk(g["G"], g["Q"], float(g["tau"]), int(g["k"]), True)
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(cnt, g["count"])
+
+
+def test_warp_restatements_match_cv2_golden(golden_align):
+    g = golden_align
+    for i in range(len(g["frame_idx"])):
+        img = g["frames"][g["frame_idx"][i]]
+        a = o.warp_affine_fixed(img, g["M"][i])
+        c = oc.warp_affine(img, g["M"][i])
+        assert hashlib.sha256(a.tobytes()).hexdigest() == str(g["sha_aligned"][i])
+        assert hashlib.sha256(c.tobytes()).hexdigest() == str(g["sha_aligned"][i])
+        b = o.blob_from_aligned(a)
+        assert hashlib.sha256(b.tobytes()).hexdigest() == str(g["sha_blob"][i])
+        assert np.array_equal(oc.blob(c).astype(np.float16), b)
+    assert np.allclose(np.stack([o.estimate_norm(l) for l in g["lmk"]]), g["M"], rtol=0, atol=1e-9)
+
+
+def test_warp_restatement_matches_installed_cv2_live():
+    cv2 = pytest.importorskip("cv2")
+    frames = o.synth_frames(1, 360, 640, seed=3)
+    fi, lm = o.synth_detections(1, 40, 360, 640, seed=11, sigma_range=(0.3, 1.5), oob_frac=0.2)
+    for i in range(len(fi)):
+        M = o.estimate_norm(lm[i])
+        want = cv2.warpAffine(frames[0], M, (112, 112), borderValue=0.0)
+        assert np.array_equal(o.warp_affine_fixed(frames[0], M), want)
+        assert np.array_equal(oc.warp_affine(frames[0], M), want)
+        blob = cv2.dnn.blobFromImages([want], 1.0 / 127.5, (112, 112), (127.5, 127.5, 127.5), swapRB=True)[0]
+        assert np.array_equal(o.blob_from_aligned(want), blob.astype(np.float16))
+
+
+def test_norm_lut_matches_cv2_golden(golden_align):
+    v = np.arange(256, dtype=np.float32)
+    lut = (v - np.float32(127.5)) * np.float32(1.0 / 127.5)
+    assert np.array_equal(lut, golden_align["lut_f32"])
+    assert np.array_equal(lut.astype(np.float16), golden_align["lut_f16"])
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+def test_live_reference_agrees_with_np_oracle():
+    fs, ENC, _ = ref_loader.load_reference()
+    G = o.synth_l2_gallery(300, 128, seed=5)
+    Q, _ = o.synth_l2_queries(G, 6, seed=6)
+    ENC.clear()
+    for i, g in enumerate(G):
+        ENC["id%07d" % i] = g.tolist()
+    try:
+        fs.tolerance = 0.6
+        for q in Q:
+            assert fs.compare_faces(q) == o.compare_faces(ENC, q, 0.6)
+        assert fs.batch_compare_faces(list(Q)) == o.batch_compare_faces(ENC, list(Q), 0.6)
+    finally:
+        ENC.clear()
