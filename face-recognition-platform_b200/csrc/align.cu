@@ -130,7 +130,9 @@ __device__ __forceinline__ TileMeta stage_tile(const AlignArgs& a, const uint8_t
     const int nchunk = (byte_hi - m.bo + 15) >> 4;
     const int nrows = sy_max + 2 - sy_min;
     m.pitch = nchunk * 16;
-    m.direct = (!a.aligned16) || (m.pitch * nrows + 16 > kTileBuf) || nchunk > 64 || nrows <= 0;
+    // coordinates near the int16 saturation of cv::remap's xy map are handled tap by tap
+    const bool far = sx_min < -30000 || sx_max > 30000 || sy_min < -30000 || sy_max > 30000;
+    m.direct = (!a.aligned16) || far || (m.pitch * nrows + 16 > kTileBuf) || nchunk > 64 || nrows <= 0;
     if (m.direct) return m;
     int sh = 0;
     while ((1 << sh) < nchunk) ++sh;

@@ -29,6 +29,18 @@ void configure_pool(int device) {
 
 int pick_kp(int k) { return k <= 10 ? 16 : (k <= 24 ? 32 : 64); }
 
+// optional per-kernel timing of the last match of the calling thread (bench roofline)
+std::atomic<int> g_profile{0};
+thread_local bool t_profile_valid = false;
+cudaEvent_t* profile_events() {
+    static thread_local cudaEvent_t ev[4] = {};
+    if (!ev[0]) {
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) { cudaGetLastError(); ev[0] = nullptr; return nullptr; }
+    }
+    return ev;
+}
+
 __global__ void fill_empty_kernel(int64_t* idx, float* score, int32_t* count, int32_t* status, int B, int k) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * k) { idx[i] = -1; score[i] = __int_as_float(0x7fc00000); }
@@ -74,12 +86,16 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
     uint64_t* cand = reinterpret_cast<uint64_t*>(ws + qprep_bytes + q16_bytes + qp_bytes);
 
     int rc = FRP_OK;
+    const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+    cudaEvent_t* ev = prof ? profile_events() : nullptr;
     if (use_gemm) {
         // padded query rows (B..ceil128) must be zero for the MMA tile
         cudaError_t e = cudaMemsetAsync(q16, 0, q16_bytes, st);
         if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = FRP_E_CUDA; }
     }
+    if (ev) cudaEventRecord(ev[0], st);
     if (!rc) rc = launch_prep_queries(g, q_dev, B, tau, flags, ec, qprep, use_gemm ? q16 : nullptr, qp, st);
+    if (ev) cudaEventRecord(ev[1], st);
     if (!rc) {
         if (use_gemm) {
             rc = launch_match_gemm(g, q16, qp, B, KP, cand, nlists, st);
@@ -89,8 +105,10 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
             set_match_path(exact ? "scan_f32" : "scan_f16");
         }
     }
+    if (ev) cudaEventRecord(ev[2], st);
     if (!rc) rc = launch_rerank(g, qprep, qp, B, k, KP, flags, tau, cand, nlists, out_idx, out_score,
                                 out_count, out_status, st);
+    if (ev) { cudaEventRecord(ev[3], st); t_profile_valid = true; }
     cudaFreeAsync(ws, st);
     return rc;
 }
@@ -126,6 +144,26 @@ cudaStream_t thread_stream(int device) {
 using namespace frp;
 
 extern "C" {
+
+int frp_profile_enable(int on) {
+    g_profile.store(on ? 1 : 0);
+    return FRP_OK;
+}
+
+int frp_profile_last(float* prep_ms, float* prefilter_ms, float* rerank_ms) {
+    if (!t_profile_valid) { set_error("frp_profile_last: no profiled match on this thread"); return FRP_E_INVALID; }
+    cudaEvent_t* ev = profile_events();
+    if (!ev) { set_error("frp_profile_last: events unavailable"); return FRP_E_CUDA; }
+    FRP_CUDA(cudaEventSynchronize(ev[3]));
+    float a = 0, b = 0, c = 0;
+    FRP_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    FRP_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+    FRP_CUDA(cudaEventElapsedTime(&c, ev[2], ev[3]));
+    if (prep_ms) *prep_ms = a;
+    if (prefilter_ms) *prefilter_ms = b;
+    if (rerank_ms) *rerank_ms = c;
+    return FRP_OK;
+}
 
 int frp_match_device(frp_gallery_t* g, const float* queries_dev, int B, double tau, int k, int flags,
                      int64_t* out_idx_dev, float* out_score_dev, int32_t* out_count_dev,

@@ -163,7 +163,10 @@ class GalleryDict:
     embedding length is not known before)."""
 
     def __init__(self, metric: int = METRIC_L2, device: int = 0, keep_host: bool = True,
-                 compact_ratio: float = 0.5):
+                 compact_ratio: float = 0.5, gallery_factory=None):
+        # gallery_factory(dim, metric, device) -> Gallery-like; the tests inject a host
+        # stand-in to exercise the dict bookkeeping without a GPU
+        self._factory = gallery_factory or Gallery
         self.metric = metric
         self.device = device
         self.keep_host = keep_host
@@ -190,7 +193,7 @@ class GalleryDict:
 
     def _ensure(self, dim: int) -> Gallery:
         if self._gallery is None:
-            self._gallery = Gallery(dim, self.metric, self.device)
+            self._gallery = self._factory(dim, self.metric, self.device)
         elif self._gallery.dim != dim:
             raise ValueError("embedding length %d does not match the gallery's %d" % (dim, self._gallery.dim))
         return self._gallery

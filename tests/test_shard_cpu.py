@@ -1,0 +1,96 @@
+"""N>1 path on CPU: world_size-2 gloo run of ShardedMatcher's partition / pack /
+all-gather / merge plumbing.  The two CUDA pieces (local match, merge) are injected
+with oracle-based stand-ins here; the real kernels are covered by the -m gpu tests."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        for p in (os.path.join(ROOT, "face-recognition-platform_b200"), os.path.join(ROOT, "oracle")):
+            sys.path.insert(0, p)
+        import torch
+        import torch.distributed as dist
+        import frp_oracle_np as o
+        from frp_b200.shard import ShardedMatcher, shard_bounds, unpack_records
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        N, D, B, k, tau = 1003, 64, 9, 6, 0.25
+        G = o.synth_cos_gallery(N, D, seed=1)
+        G[500] = G[10]            # duplicate rows on different shards: tie order = global row
+        G[900] = G[10]
+        Q, _ = o.synth_cos_queries(G, B, seed=2)
+        Q[0] = G[10]
+        lo, hi = shard_bounds(N, world, rank)
+
+        def local_match(q_dev, B_, tau_, k_, flags, idx, score, count, status, stream):
+            i, s, c = o.cos_match_topk(G[lo:hi], q_dev.numpy(), tau_, k_, True)
+            i = np.where(i >= 0, i + lo, -1)
+            idx.copy_(torch.from_numpy(i))
+            score.copy_(torch.from_numpy(np.nan_to_num(s, nan=0.0).astype(np.float32)))
+            count.copy_(torch.from_numpy(c.astype(np.int32)))
+            status.zero_()
+
+        def merge(metric, R, B_, k_, records, out_idx, out_score, out_count, any_status, stream):
+            idx, sc, cnt, st = unpack_records(records.numpy(), R, B_, k_)
+            for b in range(B_):
+                ent = [(-float(sc[r, b, j]), int(idx[r, b, j])) for r in range(R) for j in range(cnt[r, b])]
+                ent.sort()
+                ent = ent[:k_]
+                out_count[b] = len(ent)
+                for j, (ns, ii) in enumerate(ent):
+                    out_idx[b, j] = ii
+                    out_score[b, j] = -ns
+                for j in range(len(ent), k_):
+                    out_idx[b, j] = -1
+            any_status.fill_(int(st.max()))
+
+        m = ShardedMatcher(None, N, rank, world, local_match=local_match, merge=merge)
+        assert (m.lo, m.hi) == (lo, hi)
+        oi, os_, oc, anyst = m.match(torch.from_numpy(Q), tau, k, metric=1)
+        wi, ws, wc = o.cos_match_topk(G, Q, tau, k, True)
+        ok = np.array_equal(oi.numpy(), wi) and np.array_equal(oc.numpy(), wc.astype(np.int32))
+        ok = ok and int(anyst[0]) == 0
+        for b in range(B):
+            ok = ok and np.allclose(os_.numpy()[b, :wc[b]], ws[b, :wc[b]], atol=1e-6)
+        # every rank holds the same global answer
+        gathered = [torch.zeros_like(oi) for _ in range(world)]
+        dist.all_gather(gathered, oi)
+        ok = ok and all(torch.equal(g, oi) for g in gathered)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+@pytest.mark.timeout(180)
+def test_sharded_match_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for rank, ok, msg in res:
+        assert ok, "rank %d failed: %s" % (rank, msg)

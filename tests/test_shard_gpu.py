@@ -1,0 +1,86 @@
+"""Row sharding on one GPU: R "virtual shards" (R galleries with global bases) are
+matched one after another, their packed records concatenated exactly as
+ncclAllGather would, and merged by frp_merge_packed_device.  The result must not
+depend on the number of shards.  The real NCCL path is exercised by
+`bench.py --gpus N`."""
+import numpy as np
+import pytest
+import torch
+
+import frp_b200
+from frp_b200 import Gallery, METRIC_COS, METRIC_L2, MATCH_NO_THRESHOLD
+from frp_b200.shard import ShardedMatcher, record_bytes, shard_bounds
+import frp_oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded(G, Q, metric, tau, k, R, flags=0):
+    N = len(G)
+    B = len(Q)
+    dev = torch.device("cuda")
+    q_dev = torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32)).to(dev)
+    nb = record_bytes(B, k)
+    recv = torch.zeros(R * nb, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    keep = []
+    for r in range(R):
+        lo, hi = shard_bounds(N, R, r)
+        g = Gallery(G.shape[1], metric)
+        g.append(G[lo:hi])
+        m = ShardedMatcher(g, N, r, R)
+        assert (m.lo, m.hi) == (lo, hi)
+        send = recv[r * nb:(r + 1) * nb]
+        idx, score, count, status = ShardedMatcher._views(send, B, k, torch)
+        g.match_device(q_dev, B, tau, k, flags, idx, score, count, status, st)
+        keep.append(g)
+    out_idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_score = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    anyst = torch.zeros((1,), dtype=torch.int32, device=dev)
+    m._cuda_merge(metric, R, B, k, recv, out_idx, out_score, out_count, anyst, st)
+    torch.cuda.synchronize()
+    return out_idx.cpu().numpy(), out_score.cpu().numpy(), out_count.cpu().numpy(), int(anyst.item())
+
+
+@pytest.mark.parametrize("metric", [METRIC_COS, METRIC_L2])
+def test_result_is_independent_of_shard_count(metric):
+    N, D, B, k = 20_011, 128 if metric == METRIC_L2 else 512, 6, 10
+    if metric == METRIC_COS:
+        G = o.synth_cos_gallery(N, D, seed=1)
+        Q, _ = o.synth_cos_queries(G, B, seed=2)
+        tau = 0.3
+        G[15_000] = G[100]
+        G[19_999] = G[100]          # ties across shards resolve by global row
+        Q[0] = G[100]
+        widx, wsc, wcnt = o.cos_match_topk(G, Q, tau, k, True)
+    else:
+        G = o.synth_l2_gallery(N, D, seed=3).astype(np.float32)
+        Q, _ = o.synth_l2_queries(G.astype(np.float64), B, seed=4)
+        Q = Q.astype(np.float32)
+        tau = 0.6
+        widx, wsc, wcnt = o.l2_match_topk(G, Q, tau, k, True)
+    base = None
+    for R in (1, 2, 3, 8):
+        idx, sc, cnt, anyst = _sharded(G, Q, metric, tau, k, R)
+        assert anyst == 0
+        assert np.array_equal(cnt, wcnt.astype(np.int32))
+        assert np.array_equal(idx, widx)
+        for b in range(B):
+            assert np.abs(sc[b, :cnt[b]] - wsc[b, :cnt[b]]).max(initial=0) < 2e-6
+        if base is None:
+            base = (idx, sc, cnt)
+        else:
+            assert np.array_equal(idx, base[0]) and np.array_equal(sc, base[1], equal_nan=True)
+
+
+def test_single_rank_sharded_matcher_runs_end_to_end():
+    G = o.synth_cos_gallery(5000, 512, seed=5)
+    Q, _ = o.synth_cos_queries(G, 4, seed=6)
+    g = Gallery(512, METRIC_COS)
+    g.append(G)
+    m = ShardedMatcher(g, 5000, 0, 1)
+    idx, sc, cnt, anyst = m.match(torch.from_numpy(Q).cuda(), 0.3, 5, MATCH_NO_THRESHOLD)
+    torch.cuda.synchronize()
+    widx, wsc, wcnt = o.cos_match_topk(G, Q, 0.3, 5, False)
+    assert np.array_equal(idx.cpu().numpy(), widx) and int(anyst.item()) == 0
