@@ -317,16 +317,29 @@ __global__ void estimate_norm_kernel(const float* __restrict__ lmk, int n, doubl
     for (int j = 0; j < 6; ++j) M[(size_t)i * 6 + j] = m[j];
 }
 
+std::atomic<int> g_align_profile{0};
+thread_local cudaEvent_t t_align_ev[2] = {};
+thread_local bool t_align_valid = false;
+
 int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, size_t stride,
                       const int32_t* frame_idx, const float* lmk, const double* M, int n,
                       uint16_t* out_blob, uint8_t* out_aligned, cudaStream_t st) {
     if (n == 0) return FRP_OK;
-    cudaDeviceProp p;
-    FRP_CUDA(cudaGetDeviceProperties(&p, device));
-    if (p.major != 10) {
-        set_error("device %d is sm_%d%d; built for sm_100a only (no fallback)", device, p.major, p.minor);
+    // device attributes are cached: cudaGetDeviceProperties costs milliseconds per call
+    static int s_major[16] = {}, s_sms[16] = {};
+    const int di = (device >= 0 && device < 16) ? device : 0;
+    if (!s_sms[di]) {
+        int mj = 0, sms = 0;
+        FRP_CUDA(cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, device));
+        FRP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        s_major[di] = mj;
+        s_sms[di] = sms;
+    }
+    if (s_major[di] != 10) {
+        set_error("device %d is sm_%dx; built for sm_100a only (no fallback)", device, s_major[di]);
         return FRP_E_NODEVICE;
     }
+    const bool prof = g_align_profile.load(std::memory_order_relaxed) != 0;
     int* counter = nullptr;
     FRP_CUDA(cudaMallocAsync((void**)&counter, sizeof(int), st));
     FRP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
@@ -346,9 +359,14 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     }
     const int items = n * kItemsPerCrop;
     int grid = (items + kWarps - 1) / kWarps;
-    if (grid > p.multiProcessorCount) grid = p.multiProcessorCount;
+    if (grid > s_sms[di]) grid = s_sms[di];
+    if (prof) {
+        if (!t_align_ev[0]) { cudaEventCreate(&t_align_ev[0]); cudaEventCreate(&t_align_ev[1]); }
+        cudaEventRecord(t_align_ev[0], st);
+    }
     align_kernel<<<grid, kWarps * 32, smem, st>>>(a);
     FRP_CHECK_LAUNCH();
+    if (prof) { cudaEventRecord(t_align_ev[1], st); t_align_valid = true; }
     FRP_CUDA(cudaFreeAsync(counter, st));
     return FRP_OK;
 }
@@ -359,6 +377,18 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
 using namespace frp;
 
 extern "C" {
+
+int frp_profile_align_enable(int on) {
+    g_align_profile.store(on ? 1 : 0);
+    return FRP_OK;
+}
+
+int frp_profile_align_last(float* kernel_ms) {
+    if (!t_align_valid || !kernel_ms) { set_error("frp_profile_align_last: no profiled call on this thread"); return FRP_E_INVALID; }
+    FRP_CUDA(cudaEventSynchronize(t_align_ev[1]));
+    FRP_CUDA(cudaEventElapsedTime(kernel_ms, t_align_ev[0], t_align_ev[1]));
+    return FRP_OK;
+}
 
 int frp_align_device(int device, const uint8_t* frames_dev, int F, int H, int W, size_t stride,
                      const int32_t* frame_idx_dev, const float* lmk_dev, const double* M_dev, int n,

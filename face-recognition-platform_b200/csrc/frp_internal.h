@@ -105,7 +105,7 @@ int launch_match_scan(const frp_gallery* g, bool use_master, const float* qprep,
 
 // tcgen05 prefilter (B > 4): same candidate-list contract.
 bool gemm_supported(const frp_gallery* g);
-int gemm_num_lists(const frp_gallery* g);
+int gemm_num_lists(const frp_gallery* g, int B);
 int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP,
                       uint64_t* cand, int nlists, cudaStream_t st);
 

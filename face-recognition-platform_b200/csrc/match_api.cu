@@ -61,7 +61,7 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
     }
     const bool exact = (flags & FRP_MATCH_FORCE_EXACT) != 0;
     bool use_gemm = false;
-    if (!exact && gemm_supported(g)) {
+    if (!exact && KP <= 32 && gemm_supported(g)) {
         if (flags & FRP_MATCH_FORCE_GEMM) use_gemm = true;
         else if (!(flags & FRP_MATCH_FORCE_SCAN) && B > 4) use_gemm = true;
     }
@@ -69,7 +69,7 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
         set_error("frp_match: tcgen05 path not available for this gallery (dimp=%d)", g->dimp);
         return FRP_E_UNSUPPORTED;
     }
-    const int nlists = use_gemm ? gemm_num_lists(g) : scan_num_lists(g, exact);
+    const int nlists = use_gemm ? gemm_num_lists(g, B) : scan_num_lists(g, exact);
     const float ec = exact ? eps_coeff_scan_f32(g->dimp)
                            : (use_gemm ? eps_coeff_gemm_f16(g->dimp) : eps_coeff_scan_f16(g->dimp));
 

@@ -1,15 +1,374 @@
-// K4 — tcgen05/TMEM matcher (placeholder until the kernel lands; the dispatcher
-// routes every batch through the streaming scan while gemm_supported() is false).
+// K4 — tcgen05/TMEM 1:N matcher for query batches B > 4.
+//
+// Replaces the per-query Python loop of batch_compare_faces
+// (backend/app/services/face_service.py:448-481: B x face_distance + `<=`) and the
+// cosine 1:N of insightface compute_sim by ONE dense contraction S = Q . G^T on the
+// 5th-gen tensor cores with the distance/threshold/top-k fused into the epilogue:
+// scores never leave the SM.
+//
+// Operand roles: A = 128 queries (M, resident in shared memory for the whole kernel),
+// B = a 256-row gallery tile (N), K = dimp in blocks of 64 halfs (one 128-byte
+// swizzle span).  D[128 x 256] fp32 lives in TMEM: lane = query, column = gallery row,
+// so each epilogue thread owns ONE query and scans its 256 scores per tile against a
+// running cut, keeping a sorted top-KP list in registers (no cross-thread traffic).
+//
+// Warp roles (192 threads, one CTA per SM, persistent over its gallery tiles):
+//   warp 0   TMA producer: queries once, then the gallery ring (cp.async.bulk.tensor
+//            2-D, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1,
+//            kind::f16, M=128 N=256 K=16), tcgen05.commit -> smem-slot / TMEM-stage
+//            mbarriers
+//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 of their TMEM lane quadrant, cut test,
+//            register top-KP insert; double-buffered against the MMA through two
+//            256-column accumulator stages.
+// Output contract is the scan kernel's: cand[B][nlists][KP] u64 keys.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "frp_device.cuh"
 #include "frp_internal.h"
 
 namespace frp {
 
-bool gemm_supported(const frp_gallery* /*g*/) { return false; }
-int gemm_num_lists(const frp_gallery* g) { return g->sm_count; }
-int launch_match_gemm(frp_gallery* /*g*/, const __half* /*q16*/, const QParams* /*qp*/, int /*B*/,
-                      int /*KP*/, uint64_t* /*cand*/, int /*nlists*/, cudaStream_t /*st*/) {
-    set_error("tcgen05 matcher not built");
-    return FRP_E_UNSUPPORTED;
+namespace {
+
+constexpr int kTileM = 128;        // queries per CTA
+constexpr int kTileN = 256;        // gallery rows per MMA tile
+constexpr int kBlockK = 64;        // halfs per K block (128-byte swizzle span)
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kABlockBytes = kTileM * kBlockK * 2;   // 16 KB
+constexpr int kBStageBytes = kTileN * kBlockK * 2;   // 32 KB
+constexpr int kMaxStages = 6;
+constexpr int kAccCols = kTileN;                     // fp32 accumulator columns per stage
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmArgs {
+    const uint8_t* alive;
+    const float* norm2;
+    const QParams* qp;
+    uint64_t* cand;
+    uint32_t rows;
+    uint32_t ntiles;
+    int B;
+    int nkb;       // K blocks (dimp / 64)
+    int stages;    // gallery ring depth
+    int metric;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+// start address >> 4 | LBO = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                  const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B operands
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)a.nkb * kABlockBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)a.stages * kBStageBytes);
+    uint64_t* full_bar = bars;                       // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
+    uint64_t* afull_bar = bars + 2 * kMaxStages + 4;   // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qgroup = blockIdx.y;
+    const uint32_t my_tiles = (a.ntiles > blockIdx.x) ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_g);
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(afull_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(afull_bar, (uint32_t)a.nkb * kABlockBytes);
+            for (int kb = 0; kb < a.nkb; ++kb)
+                tma_load_2d(&tmap_q, afull_bar, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK, qgroup * kTileM);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const int row0 = (int)((blockIdx.x + i * gridDim.x) * kTileN);
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(&full_bar[s], kBStageBytes);
+                    tma_load_2d(&tmap_g, &full_bar[s], smem_b + (size_t)s * kBStageBytes, kb * kBlockK, row0);
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        mbar_wait(afull_bar, 0);
+        tc_fence_after();
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t as = i & 1;
+            mbar_wait(&tempty_bar[as], ((i >> 1) & 1) ^ 1);     // epilogue drained this TMEM stage
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * kAccCols;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(&full_bar[s], ph);                    // TMA landed this gallery K block
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = a_base + (uint32_t)kb * kABlockBytes;
+                    const uint32_t b_addr = b_base + (uint32_t)s * kBStageBytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK * 2);
+                        const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
+                        umma_f16(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                  // frees the smem slot when the MMAs retire
+                    if (kb == a.nkb - 1) umma_commit(&tfull_bar[as]);   // accumulator ready
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue: one query per thread =================
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int q = qgroup * kTileM + quad * 32 + lane;
+        const bool valid_q = q < a.B;
+        const float ninf = __int_as_float(0xff800000);
+        float cut0 = valid_q ? a.qp[q].cut0 : __int_as_float(0x7f800000);
+        float cut = cut0;
+        float ls[KP];
+        uint32_t lr[KP];
+#pragma unroll
+        for (int p = 0; p < KP; ++p) { ls[p] = ninf; lr[p] = 0xffffffffu; }
+        const bool is_l2 = (a.metric == FRP_METRIC_L2);
+
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t as = i & 1;
+            const uint32_t row0 = (blockIdx.x + i * gridDim.x) * kTileN;
+            mbar_wait(&tfull_bar[as], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols;
+#pragma unroll 1
+            for (int c = 0; c < kTileN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float s = __uint_as_float(v[j]);
+                    const uint32_t row = row0 + c + j;
+                    if (is_l2) s = 2.f * s - ((row < a.rows) ? __ldg(a.norm2 + row) : 0.f);
+                    if (s >= cut && row < a.rows) {
+                        if (a.alive[row]) {
+                            float cs = s;
+                            uint32_t cr = row;
+#pragma unroll
+                            for (int p = 0; p < KP; ++p) {
+                                const bool gt = cs > ls[p];
+                                const float ts = gt ? ls[p] : cs;
+                                const uint32_t tr = gt ? lr[p] : cr;
+                                ls[p] = gt ? cs : ls[p];
+                                lr[p] = gt ? cr : lr[p];
+                                cs = ts;
+                                cr = tr;
+                            }
+                            cut = fmaxf(cut0, ls[KP - 1]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (valid_q) {
+            uint64_t* out = a.cand + ((size_t)q * gridDim.x + blockIdx.x) * KP;
+#pragma unroll
+            for (int p = 0; p < KP; ++p) out[p] = (lr[p] != 0xffffffffu) ? make_key(ls[p], lr[p]) : 0ull;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    });
+    return fn;
+}
+
+// 2-D fp16 row-major [rows][dimp] tensor, box = [box_rows][64], 128-byte swizzle
+int encode_map(CUtensorMap* map, const void* base, uint64_t rows, int dimp, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return FRP_E_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)dimp, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dimp * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FRP_E_CUDA; }
+    return FRP_OK;
+}
+
+int pick_stages(int nkb) {
+    const int budget = 227 * 1024 - 2048 - nkb * kABlockBytes;   // barriers + alignment slack
+    int st = budget / kBStageBytes;
+    if (st > kMaxStages) st = kMaxStages;
+    return st;
+}
+
+}  // namespace
+
+bool gemm_supported(const frp_gallery* g) {
+    return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
+           get_encode_fn() != nullptr;
+}
+
+static int gemm_groups(int B) { return (B + kTileM - 1) / kTileM; }
+
+int gemm_num_lists(const frp_gallery* g, int B) {
+    const int groups = gemm_groups(B);
+    int per = g->sm_count / groups;
+    if (per < 1) per = 1;
+    const uint64_t ntiles = (g->rows + kTileN - 1) / kTileN;
+    if ((uint64_t)per > ntiles) per = (int)ntiles;
+    return per;
+}
+
+int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP, uint64_t* cand,
+                      int nlists, cudaStream_t st) {
+    const int groups = gemm_groups(B);
+    const int nkb = g->dimp / kBlockK;
+    const int stages = pick_stages(nkb);
+    if (stages < 2) { set_error("match_gemm: not enough shared memory for dimp=%d", g->dimp); return FRP_E_UNSUPPORTED; }
+    CUtensorMap tq, tg;
+    int rc = encode_map(&tq, q16, (uint64_t)groups * kTileM, g->dimp, kTileM);
+    if (rc) return rc;
+    rc = encode_map(&tg, g->g16, g->rows, g->dimp, kTileN);
+    if (rc) return rc;
+    GemmArgs a;
+    a.alive = g->alive;
+    a.norm2 = g->norm2;
+    a.qp = qp;
+    a.cand = cand;
+    a.rows = (uint32_t)g->rows;
+    a.ntiles = (uint32_t)((g->rows + kTileN - 1) / kTileN);
+    a.B = B;
+    a.nkb = nkb;
+    a.stages = stages;
+    a.metric = g->metric;
+    const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256;
+    dim3 grid(nlists, groups);
+#define FRP_GEMM_LAUNCH(KP_)                                                                             \
+    {                                                                                                    \
+        static thread_local size_t configured = 0;                                                       \
+        if (configured < smem) {                                                                         \
+            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                   \
+            configured = smem;                                                                           \
+        }                                                                                                \
+        match_gemm_kernel<KP_><<<grid, kThreads, smem, st>>>(tq, tg, a);                                 \
+    }
+    if (KP == 16) FRP_GEMM_LAUNCH(16)
+    else if (KP == 32) FRP_GEMM_LAUNCH(32)
+    else { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
+#undef FRP_GEMM_LAUNCH
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
 }
 
 }  // namespace frp

@@ -72,6 +72,8 @@ SIGNATURES = {
     "frp_align_device": (_i, [_i, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "frp_profile_enable": (_i, [_i]),
     "frp_profile_last": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "frp_profile_align_enable": (_i, [_i]),
+    "frp_profile_align_last": (_i, [C.POINTER(C.c_float)]),
     "frp_kernel_launches": (_u64, []),
     "frp_last_match_path": (C.c_char_p, []),
 }

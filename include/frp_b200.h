@@ -161,6 +161,9 @@ uint64_t frp_kernel_launches(void);
  * returns the device time of its three stages in milliseconds */
 int frp_profile_enable(int on);
 int frp_profile_last(float* prep_ms, float* prefilter_ms, float* rerank_ms);
+/* same for the alignment kernel of frp_align_device */
+int frp_profile_align_enable(int on);
+int frp_profile_align_last(float* kernel_ms);
 /* name of the kernel family the last frp_match* call of this thread used:
  * "scan_f16", "scan_f32", "gemm_tcgen05" */
 const char* frp_last_match_path(void);

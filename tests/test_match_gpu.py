@@ -8,7 +8,7 @@ import pytest
 
 import frp_b200
 from frp_b200 import (FaceService, Gallery, GalleryDict, METRIC_COS, METRIC_L2, MATCH_FORCE_EXACT,
-                      MATCH_FORCE_SCAN, MATCH_NO_THRESHOLD)
+                      MATCH_FORCE_GEMM, MATCH_FORCE_SCAN, MATCH_NO_THRESHOLD)
 import frp_oracle_np as o
 
 pytestmark = pytest.mark.gpu
@@ -219,6 +219,52 @@ def test_cosine_random_vs_oracle(B):
             assert idx[b, 0] == planted[b]
 
 
+@pytest.mark.parametrize("B", [1, 7, 128, 129, 256, 300])
+def test_tcgen05_path_vs_oracle(B):
+    """The tensor-core prefilter (forced for every batch size) against the oracle, and
+    against the streaming scan path: identical indices and scores."""
+    N, D, k, tau = 50_021, 512, 10, 0.35
+    G = o.synth_cos_gallery(N, D, seed=300 + B)
+    Q, planted = o.synth_cos_queries(G, B, seed=400 + B)
+    gal = Gallery(D, METRIC_COS)
+    gal.append(G)
+    for thresholded in (True, False):
+        fl = 0 if thresholded else MATCH_NO_THRESHOLD
+        widx, wsc, wcnt = o.cos_match_topk(G, Q, tau, k, thresholded)
+        idx, sc, cnt, st = gal.match(Q, tau, k, fl | MATCH_FORCE_GEMM)
+        assert frp_b200.last_match_path() == "gemm_tcgen05"
+        assert exact_equal(idx, cnt, widx, wcnt)
+        assert np.all(st == 0)
+        i2, s2, c2, _ = gal.match(Q, tau, k, fl | MATCH_FORCE_SCAN)
+        assert np.array_equal(i2, idx) and np.array_equal(s2, sc, equal_nan=True)
+
+
+@pytest.mark.parametrize("dim,metric", [(128, METRIC_L2), (64, METRIC_COS), (256, METRIC_L2), (100, METRIC_COS)])
+def test_tcgen05_path_other_dims(dim, metric):
+    rng = np.random.default_rng(dim)
+    N, B, k = 9000, 40, 12
+    G = rng.normal(0, 0.06, (N, dim)).astype(np.float32)
+    Q = G[rng.integers(0, N, B)] + rng.normal(0, 0.03, (B, dim)).astype(np.float32)
+    gal = Gallery(dim, metric)
+    gal.append(G)
+    gal.remove(int(rng.integers(0, N)))
+    if metric == METRIC_L2:
+        S = np.stack([np.linalg.norm(G.astype(np.float64) - q.astype(np.float64), axis=1) for q in Q])
+        tau = float(np.sort(S[0])[25])
+    else:
+        S = o.cosine_scores(G, Q)
+        tau = float(np.sort(S[0])[-25])
+    a = gal.match(Q, tau, k, MATCH_FORCE_GEMM)
+    assert frp_b200.last_match_path() == "gemm_tcgen05"
+    b = gal.match(Q, tau, k, MATCH_FORCE_SCAN)
+    c = gal.match(Q, tau, k, MATCH_FORCE_EXACT)
+    for r in (b, c):
+        assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1], equal_nan=True) and np.array_equal(a[2], r[2])
+    for bq in range(B):
+        got = a[0][bq, :a[2][bq]]
+        assert np.abs(a[1][bq, :a[2][bq]] - S[bq][got]).max(initial=0) < TIGHT
+
+
 @pytest.mark.parametrize("dim", [64, 100, 128, 256, 384, 512])
 @pytest.mark.parametrize("metric", [METRIC_L2, METRIC_COS])
 def test_dims_and_metrics(dim, metric):
@@ -312,7 +358,9 @@ def test_snapshot_roundtrip(tmp_path):
     assert g2.counts() == gal.counts() and g2.metric == METRIC_COS and g2.dim == 512
     a = gal.match(Q, 0.3, 10)
     b = g2.match(Q, 0.3, 10)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[1], b[1], equal_nan=True)
+    assert a[2].sum() >= 2
 
 
 def test_concurrent_callers():
