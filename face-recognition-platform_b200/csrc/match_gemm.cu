@@ -115,7 +115,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
-template <int KP>
+template <int KP, bool IS_L2>
 __global__ void __launch_bounds__(kThreads, 1)
 match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                   const GemmArgs a) {
@@ -214,7 +214,6 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         uint32_t lr[KP];
 #pragma unroll
         for (int p = 0; p < KP; ++p) { ls[p] = ninf; lr[p] = 0xffffffffu; }
-        const bool is_l2 = (a.metric == FRP_METRIC_L2);
 
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t as = i & 1;
@@ -227,26 +226,44 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 uint32_t v[32];
                 tmem_ld32(taddr + c, v);
                 tmem_ld_wait();
+                float sv[32];
+                if (IS_L2) {
+                    // s = 2 g.q - |g|^2 ; the norm is the same address for every lane (broadcast)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float s = __uint_as_float(v[j]);
-                    const uint32_t row = row0 + c + j;
-                    if (is_l2) s = 2.f * s - ((row < a.rows) ? __ldg(a.norm2 + row) : 0.f);
-                    if (s >= cut && row < a.rows) {
-                        if (a.alive[row]) {
-                            float cs = s;
-                            uint32_t cr = row;
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t row = min(row0 + c + j, a.rows - 1);
+                        sv[j] = fmaf(2.f, __uint_as_float(v[j]), -__ldg(a.norm2 + row));
+                    }
+                } else {
 #pragma unroll
-                            for (int p = 0; p < KP; ++p) {
-                                const bool gt = cs > ls[p];
-                                const float ts = gt ? ls[p] : cs;
-                                const uint32_t tr = gt ? lr[p] : cr;
-                                ls[p] = gt ? cs : ls[p];
-                                lr[p] = gt ? cr : lr[p];
-                                cs = ts;
-                                cr = tr;
+                    for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
+                }
+                // one branch per 32 scores: a per-element branch costs a convergence
+                // barrier (BSSY/BSYNC) each and made the epilogue the bottleneck
+                float mx = sv[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sv[j]);
+                if (mx >= cut) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = sv[j];
+                        const uint32_t row = row0 + c + j;
+                        if (s >= cut && row < a.rows) {
+                            if (a.alive[row]) {
+                                float cs = s;
+                                uint32_t cr = row;
+#pragma unroll
+                                for (int p = 0; p < KP; ++p) {
+                                    const bool gt = cs > ls[p];
+                                    const float ts = gt ? ls[p] : cs;
+                                    const uint32_t tr = gt ? lr[p] : cr;
+                                    ls[p] = gt ? cs : ls[p];
+                                    lr[p] = gt ? cr : lr[p];
+                                    cs = ts;
+                                    cr = tr;
+                                }
+                                cut = fmaxf(cut0, ls[KP - 1]);
                             }
-                            cut = fmaxf(cut0, ls[KP - 1]);
                         }
                     }
                 }
@@ -353,18 +370,21 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     a.metric = g->metric;
     const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256;
     dim3 grid(nlists, groups);
-#define FRP_GEMM_LAUNCH(KP_)                                                                             \
+#define FRP_GEMM_LAUNCH(KP_, L2_)                                                                        \
     {                                                                                                    \
         static thread_local size_t configured = 0;                                                       \
         if (configured < smem) {                                                                         \
-            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                   \
+            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
             configured = smem;                                                                           \
         }                                                                                                \
-        match_gemm_kernel<KP_><<<grid, kThreads, smem, st>>>(tq, tg, a);                                 \
+        match_gemm_kernel<KP_, L2_><<<grid, kThreads, smem, st>>>(tq, tg, a);                            \
     }
-    if (KP == 16) FRP_GEMM_LAUNCH(16)
-    else if (KP == 32) FRP_GEMM_LAUNCH(32)
+    const bool l2 = (g->metric == FRP_METRIC_L2);
+    if (KP == 16 && !l2) FRP_GEMM_LAUNCH(16, false)
+    else if (KP == 16 && l2) FRP_GEMM_LAUNCH(16, true)
+    else if (KP == 32 && !l2) FRP_GEMM_LAUNCH(32, false)
+    else if (KP == 32 && l2) FRP_GEMM_LAUNCH(32, true)
     else { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
 #undef FRP_GEMM_LAUNCH
     FRP_CHECK_LAUNCH();
