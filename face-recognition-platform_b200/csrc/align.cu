@@ -6,14 +6,20 @@
 // Replaces insightface face_align.norm_crop + cv2.dnn.blobFromImages (third-party
 // code reached from backend/app/utils/deepfake_utils.py:138).
 //
-// One warp per work item (half a crop = 49 output tiles of 16x8 px).  Per tile the
-// warp stages the source bounding box of the tile into its private shared-memory
-// buffer with 128-bit cp.async copies on 16-byte aligned row segments (zero-filled
-// outside the frame = BORDER_CONSTANT 0), double buffered against the blend of the
-// previous tile; each lane then produces 4 consecutive output pixels from shared
-// memory with integer dp2a blends, maps them through a 256-entry fp16 table and
-// writes 8-byte segments of the three output planes.
+// One warp per work item (half a crop).  The crop is cut into 16 x TH output tiles
+// (TH = 16, or 8 for large faces); per tile ONE 3-D tiled TMA load
+// (cp.async.bulk.tensor, SASS UTMALDG) stages the source bounding box of the tile —
+// bytes x rows x frame, zero-filled outside the frame, which IS BORDER_CONSTANT 0 —
+// into the warp's private shared-memory buffer, double buffered against the blend of
+// the previous tile through two mbarriers.  Box sizes come from a 5x5 ladder of tensor
+// maps so small faces do not over-fetch.  Each lane then produces TH/2 consecutive
+// output pixels from shared memory with integer dp2a blends (bit-exact with cv2),
+// maps them through a 256-entry fp16 table and writes 16-byte (8-byte) segments of the
+// three output planes.  Tiles whose footprint exceeds the largest box (or frames whose
+// pitch is not 16-byte aligned) are sampled tap by tap from global memory.
+#include <cuda.h>
 #include <math.h>
+#include <string.h>
 
 #include "frp_device.cuh"
 #include "frp_internal.h"
@@ -23,16 +29,23 @@ namespace frp {
 namespace {
 
 constexpr int kOut = 112;
-constexpr int kTileW = 16, kTileH = 8;
+constexpr int kTileW = 16;
 constexpr int kTilesX = kOut / kTileW;              // 7
-constexpr int kTilesY = kOut / kTileH;              // 14
-constexpr int kTilesPerCrop = kTilesX * kTilesY;    // 98
 constexpr int kItemsPerCrop = 2;
-constexpr int kTilesPerItem = kTilesPerCrop / kItemsPerCrop;   // 49
-constexpr int kWarps = 8;
-constexpr int kTileBuf = 12 * 1024;                 // bytes per staging buffer
-constexpr int kTabInts = 4 * kOut;                  // adelta, bdelta, X0, Y0
-constexpr int kWarpSmem = kTabInts * 4 + 2 * kTileBuf + 32;
+constexpr int kWarps = 10;
+constexpr int kNumW = 5, kNumH = 5;
+__constant__ int c_box_w[kNumW] = {64, 96, 128, 176, 224};   // bytes (multiples of 16)
+__constant__ int c_box_h[kNumH] = {8, 14, 22, 34, 46};       // rows
+constexpr int kHostBoxW[kNumW] = {64, 96, 128, 176, 224};
+constexpr int kHostBoxH[kNumH] = {8, 14, 22, 34, 46};
+constexpr int kMaxBoxW = 224, kMaxBoxH = 46;
+constexpr int kBufBytes = 10368;                    // >= 224*46 + 16 slack, multiple of 128
+constexpr int kTabBytes = 4 * kOut * 4;             // adelta, bdelta, X0, Y0 (1792 = 14*128)
+constexpr int kWarpSmem = 22656;                    // tab + 2 buffers + 2 mbarriers, multiple of 128
+
+struct TmapSet {
+    CUtensorMap m[kNumW * kNumH];
+};
 
 struct AlignArgs {
     const uint8_t* frames;
@@ -45,7 +58,7 @@ struct AlignArgs {
     __half* out_blob;     // [n][3][112][112]
     uint8_t* out_aligned; // [n][112][112][3] or null
     int* counter;         // dynamic work counter
-    int aligned16;        // frames base and stride are 16-byte aligned
+    int use_tma;          // tensor maps valid (16-byte aligned base / pitch)
 };
 
 __constant__ double c_dst[10] = {
@@ -90,65 +103,60 @@ __device__ void invert_affine_dev(const double* M, double* iM) {
     iM[3] = m3;  iM[4] = A22; iM[5] = b2;
 }
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
-                 "r"(src_bytes)
-                 : "memory");
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, uint32_t dst_saddr, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_saddr), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 
 struct TileMeta {
-    int bo;        // byte offset (in the source row) of the first staged byte; multiple of 16
+    int c0;        // byte offset (in the source row) of the first staged byte
     int sy0;       // first staged source row
-    int pitch;     // staged row pitch in bytes (multiple of 16)
+    int pitch;     // staged row pitch in bytes (box width)
     int direct;    // 1: footprint did not fit -> read taps from global memory
 };
 
-__device__ __forceinline__ int floor_div16(int v) { return v >> 4; }   // arithmetic shift = floor
-
-// stage the source footprint of output tile (x0,y0) into buf
-__device__ __forceinline__ TileMeta stage_tile(const AlignArgs& a, const uint8_t* frame, const int* tab,
-                                               int x0, int y0, uint8_t* buf, int lane) {
+// choose the box for output tile (x0,y0,TH) and start its TMA load into buf
+template <int TH>
+__device__ __forceinline__ TileMeta stage_tile(const AlignArgs& a, const TmapSet& maps, const int* tab, int x0,
+                                               int y0, int frame_index, uint32_t buf_saddr, uint64_t* bar,
+                                               int lane) {
     const int* adelta = tab;
     const int* bdelta = tab + kOut;
     const int* X0 = tab + 2 * kOut;
     const int* Y0 = tab + 3 * kOut;
     const int xa = adelta[x0], xb = adelta[x0 + kTileW - 1];
     const int ya = bdelta[x0], yb = bdelta[x0 + kTileW - 1];
-    const int Xa = X0[y0], Xb = X0[y0 + kTileH - 1];
-    const int Ya = Y0[y0], Yb = Y0[y0 + kTileH - 1];
+    const int Xa = X0[y0], Xb = X0[y0 + TH - 1];
+    const int Ya = Y0[y0], Yb = Y0[y0 + TH - 1];
     const int sx_min = (min(Xa, Xb) + min(xa, xb)) >> 10;
     const int sx_max = (max(Xa, Xb) + max(xa, xb)) >> 10;
     const int sy_min = (min(Ya, Yb) + min(ya, yb)) >> 10;
     const int sy_max = (max(Ya, Yb) + max(ya, yb)) >> 10;
     TileMeta m;
-    m.bo = floor_div16(3 * sx_min) * 16;
+    m.c0 = (3 * sx_min) & ~15;                       // TMA needs the inner coordinate 16-byte aligned (floor, also for negatives)
     m.sy0 = sy_min;
-    const int byte_hi = 3 * (sx_max + 2);
-    const int nchunk = (byte_hi - m.bo + 15) >> 4;
-    const int nrows = sy_max + 2 - sy_min;
-    m.pitch = nchunk * 16;
+    const int need_w = 3 * (sx_max + 2) - m.c0;       // bytes: taps sx .. sx_max+1 plus the alignment slack
+    const int need_h = sy_max + 2 - sy_min;         // rows:  taps sy .. sy_max+1
     // coordinates near the int16 saturation of cv::remap's xy map are handled tap by tap
     const bool far = sx_min < -30000 || sx_max > 30000 || sy_min < -30000 || sy_max > 30000;
-    m.direct = (!a.aligned16) || far || (m.pitch * nrows + 16 > kTileBuf) || nchunk > 64 || nrows <= 0;
-    if (m.direct) return m;
-    int sh = 0;
-    while ((1 << sh) < nchunk) ++sh;
-    const int total = nrows << sh;
-    const int row_bytes = 3 * a.W;
-    for (int i = lane; i < total; i += 32) {
-        const int r = i >> sh;
-        const int c = i & ((1 << sh) - 1);
-        if (c < nchunk) {
-            const int sy = sy_min + r;
-            const int gb = m.bo + 16 * c;
-            int valid = 0;
-            if (sy >= 0 && sy < a.H && gb >= 0) valid = min(16, max(0, row_bytes - gb));
-            const uint8_t* src = valid ? (frame + (size_t)sy * a.stride + gb) : frame;
-            cp_async16(buf + r * m.pitch + 16 * c, src, valid);
-        }
+    int wi = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < kNumW - 1; ++i) wi += (need_w > c_box_w[i]) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < kNumH - 1; ++i) hi += (need_h > c_box_h[i]) ? 1 : 0;
+    m.pitch = c_box_w[wi];
+    m.direct = (!a.use_tma) || far || need_w > kMaxBoxW || need_h > kMaxBoxH || need_h <= 0;
+    if (!m.direct && lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(c_box_w[wi] * c_box_h[hi]));
+        tma_load_3d(&maps.m[hi * kNumW + wi], bar, buf_saddr, m.c0, m.sy0, frame_index);
     }
     return m;
 }
@@ -160,8 +168,127 @@ __device__ __forceinline__ unsigned tap_global(const AlignArgs& a, const uint8_t
     return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 1) align_kernel(const AlignArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+// blend: 4 taps as (row0: B0 G0 R0 B1 | G1 R1 . .), (row1 likewise) -> B, G, R in [0,255]
+__device__ __forceinline__ void blend_px(unsigned p0lo, unsigned p0hi, unsigned p1lo, unsigned p1hi, unsigned fx,
+                                         unsigned fy, unsigned& vB, unsigned& vG, unsigned& vR) {
+    // (B0,B1,G0,G1) and (R0,R1) byte pairs for the two 16-bit x 8-bit dot products
+    const unsigned bg0 = __byte_perm(p0lo, p0hi, 0x4130), rr0 = __byte_perm(p0lo, p0hi, 0x0052);
+    const unsigned bg1 = __byte_perm(p1lo, p1hi, 0x4130), rr1 = __byte_perm(p1lo, p1hi, 0x0052);
+    // weights: w00=(32-fx)(32-fy)*32, w01=fx(32-fy)*32, w10=(32-fx)fy*32, w11=fx*fy*32
+    const unsigned P = fx * 0xFFFFu + 32u;          // (32-fx) | fx<<16
+    const unsigned W0 = ((32u - fy) * P) << 5;      // w00 | w01<<16
+    const unsigned W1 = (fy * P) << 5;              // w10 | w11<<16
+    unsigned accB = __dp2a_lo(W0, bg0, 16384u); accB = __dp2a_lo(W1, bg1, accB);
+    unsigned accG = __dp2a_hi(W0, bg0, 16384u); accG = __dp2a_hi(W1, bg1, accG);
+    unsigned accR = __dp2a_lo(W0, rr0, 16384u); accR = __dp2a_lo(W1, rr1, accR);
+    vB = accB >> 15; vG = accG >> 15; vR = accR >> 15;
+}
+
+// one output tile: each lane produces PXL = TH/2 consecutive pixels of one output row
+template <int TH>
+__device__ __forceinline__ void blend_tile(const AlignArgs& a, const uint8_t* frame, const int* tab,
+                                           const TileMeta& tm, uint32_t buf_saddr, int x0, int y0, int lane,
+                                           const unsigned short* lut, __half* oblob, uint8_t* oal) {
+    constexpr int PXL = TH / 2;
+    constexpr int LPR = kTileW / PXL;               // lanes per output row
+    const int y = y0 + lane / LPR;
+    const int xs = x0 + (lane % LPR) * PXL;
+    const int Xy = tab[2 * kOut + y], Yy = tab[3 * kOut + y];
+    int adv[PXL], bdv[PXL];
+#pragma unroll
+    for (int j = 0; j < PXL; j += 4) {
+        const int4 ad = *reinterpret_cast<const int4*>(tab + xs + j);
+        const int4 bd = *reinterpret_cast<const int4*>(tab + kOut + xs + j);
+        adv[j] = ad.x; adv[j + 1] = ad.y; adv[j + 2] = ad.z; adv[j + 3] = ad.w;
+        bdv[j] = bd.x; bdv[j + 1] = bd.y; bdv[j + 2] = bd.z; bdv[j + 3] = bd.w;
+    }
+    unsigned vB[PXL], vG[PXL], vR[PXL];
+    if (!tm.direct) {
+        const int base = -tm.sy0 * tm.pitch - tm.c0;
+#pragma unroll
+        for (int j = 0; j < PXL; ++j) {
+            const int X = (Xy + adv[j]) >> 5, Y = (Yy + bdv[j]) >> 5;
+            const int sx = X >> 5, sy = Y >> 5;
+            const unsigned fx = X & 31, fy = Y & 31;
+            const int off = sy * tm.pitch + 3 * sx + base;
+            const uint32_t w0 = buf_saddr + (off & ~3);
+            const uint32_t w1 = w0 + tm.pitch;
+            const unsigned shf = (off & 3) * 8;
+            const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32(w0 + 8);
+            const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32(w1 + 8);
+            blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
+                     __funnelshift_r(b1, b2, shf), fx, fy, vB[j], vG[j], vR[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PXL; ++j) {
+            const int X = (Xy + adv[j]) >> 5, Y = (Yy + bdv[j]) >> 5;
+            const int sx = max(-32768, min(32767, X >> 5));
+            const int sy = max(-32768, min(32767, Y >> 5));
+            const unsigned fx = X & 31, fy = Y & 31;
+            const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
+            const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
+            blend_px(t00 | (t01 << 24), t01 >> 8, t10 | (t11 << 24), t11 >> 8, fx, fy, vB[j], vG[j], vR[j]);
+        }
+    }
+    // ---- normalise through the table, BGR->RGB planes, vector stores ----
+    const size_t o = (size_t)y * kOut + xs;
+    unsigned r[PXL / 2], g[PXL / 2], b[PXL / 2];
+#pragma unroll
+    for (int j = 0; j < PXL / 2; ++j) {
+        r[j] = (unsigned)lut[vR[2 * j]] | ((unsigned)lut[vR[2 * j + 1]] << 16);
+        g[j] = (unsigned)lut[vG[2 * j]] | ((unsigned)lut[vG[2 * j + 1]] << 16);
+        b[j] = (unsigned)lut[vB[2 * j]] | ((unsigned)lut[vB[2 * j + 1]] << 16);
+    }
+    if (PXL == 8) {
+        *reinterpret_cast<uint4*>(oblob + o) = make_uint4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<uint4*>(oblob + (size_t)kOut * kOut + o) = make_uint4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<uint4*>(oblob + (size_t)2 * kOut * kOut + o) = make_uint4(b[0], b[1], b[2], b[3]);
+    } else {
+        *reinterpret_cast<uint2*>(oblob + o) = make_uint2(r[0], r[1]);
+        *reinterpret_cast<uint2*>(oblob + (size_t)kOut * kOut + o) = make_uint2(g[0], g[1]);
+        *reinterpret_cast<uint2*>(oblob + (size_t)2 * kOut * kOut + o) = make_uint2(b[0], b[1]);
+    }
+    if (oal) {
+        uint8_t* p = oal + o * 3;
+#pragma unroll
+        for (int j = 0; j < PXL; ++j) {
+            p[3 * j] = (uint8_t)vB[j]; p[3 * j + 1] = (uint8_t)vG[j]; p[3 * j + 2] = (uint8_t)vR[j];
+        }
+    }
+}
+
+// all tiles [t_begin, t_end) of one crop with tile height TH, double buffered
+template <int TH>
+__device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& maps, const uint8_t* frame, int fi,
+                                          const int* tab, uint32_t buf_saddr0, uint64_t* bars, uint32_t& parity,
+                                          int t_begin, int t_end, int lane, const unsigned short* lut,
+                                          __half* oblob, uint8_t* oal) {
+    TileMeta cur, nxt;
+    cur = stage_tile<TH>(a, maps, tab, (t_begin % kTilesX) * kTileW, (t_begin / kTilesX) * TH, fi, buf_saddr0,
+                         &bars[0], lane);
+    nxt = cur;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int b = (t - t_begin) & 1;
+        if (t + 1 < t_end) {
+            const int tn = t + 1;
+            nxt = stage_tile<TH>(a, maps, tab, (tn % kTilesX) * kTileW, (tn / kTilesX) * TH, fi,
+                                 buf_saddr0 + (uint32_t)((b ^ 1) * kBufBytes), &bars[b ^ 1], lane);
+        }
+        if (!cur.direct) {
+            mbar_wait(&bars[b], (parity >> b) & 1u);
+            parity ^= (1u << b);
+        }
+        blend_tile<TH>(a, frame, tab, cur, buf_saddr0 + (uint32_t)(b * kBufBytes), (t % kTilesX) * kTileW,
+                       (t / kTilesX) * TH, lane, lut, oblob, oal);
+        __syncwarp();      // every lane is done with buffer b before it is refilled
+        cur = nxt;
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 1)
+align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __half s_lut[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // (v - 127.5) * float(1/127.5) in fp32, as cv2.dnn.blobFromImages computes it
@@ -169,11 +296,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) align_kernel(const AlignArgs a
         const float f = __fmul_rn(__fsub_rn((float)threadIdx.x, 127.5f), (float)(1.0 / 127.5));
         s_lut[threadIdx.x] = __float2half_rn(f);
     }
-    __syncthreads();
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t* wsm = smem + (size_t)warp * kWarpSmem;
     int* tab = reinterpret_cast<int*>(wsm);
-    uint8_t* bufs[2] = {wsm + kTabInts * 4, wsm + kTabInts * 4 + kTileBuf + 16};
+    const uint32_t buf_saddr0 = smem_u32(wsm + kTabBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kTabBytes + 2 * kBufBytes);
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
     const unsigned short* lut = reinterpret_cast<const unsigned short*>(s_lut);
+    uint32_t parity = 0;
 
     const int nitems = a.n * kItemsPerCrop;
     for (;;) {
@@ -182,7 +317,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) align_kernel(const AlignArgs a
         item = __shfl_sync(FRP_FULL_MASK, item, 0);
         if (item >= nitems) break;
         const int crop = item / kItemsPerCrop;
-        const int tile_begin = (item % kItemsPerCrop) * kTilesPerItem;
+        const int half = item % kItemsPerCrop;
 
         // ---- per-crop setup (every lane computes the same matrix) ----
         double M[6], iM[6];
@@ -218,91 +353,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) align_kernel(const AlignArgs a
         __half* oblob = a.out_blob + (size_t)crop * 3 * kOut * kOut;
         uint8_t* oal = a.out_aligned ? a.out_aligned + (size_t)crop * kOut * kOut * 3 : nullptr;
 
-        TileMeta cur, nxt;
-        {
-            const int t = tile_begin;
-            cur = stage_tile(a, frame, tab, (t % kTilesX) * kTileW, (t / kTilesX) * kTileH, bufs[0], lane);
-            cp_async_commit();
-        }
-        for (int tt = 0; tt < kTilesPerItem; ++tt) {
-            const int t = tile_begin + tt;
-            if (tt + 1 < kTilesPerItem) {
-                const int tn = t + 1;
-                nxt = stage_tile(a, frame, tab, (tn % kTilesX) * kTileW, (tn / kTilesX) * kTileH,
-                                 bufs[(tt + 1) & 1], lane);
-                cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-
-            // ---- blend 4 consecutive output pixels per lane ----
-            const uint8_t* buf = bufs[tt & 1];
-            const int x0 = (t % kTilesX) * kTileW, y0 = (t / kTilesX) * kTileH;
-            const int y = y0 + (lane >> 2);
-            const int xs = x0 + (lane & 3) * 4;
-            const int Xy = tab[2 * kOut + y], Yy = tab[3 * kOut + y];
-            const int4 ad = *reinterpret_cast<const int4*>(tab + xs);
-            const int4 bd = *reinterpret_cast<const int4*>(tab + kOut + xs);
-            const int adv[4] = {ad.x, ad.y, ad.z, ad.w};
-            const int bdv[4] = {bd.x, bd.y, bd.z, bd.w};
-            unsigned vB[4], vG[4], vR[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int X = (Xy + adv[j]) >> 5, Y = (Yy + bdv[j]) >> 5;
-                const int sx = max(-32768, min(32767, X >> 5));
-                const int sy = max(-32768, min(32767, Y >> 5));
-                const unsigned fx = X & 31, fy = Y & 31;
-                unsigned p0lo, p0hi, p1lo, p1hi;   // row0: B0 G0 R0 B1 | G1 R1 . .  ; row1 likewise
-                if (!cur.direct) {
-                    const int addr = (sy - cur.sy0) * cur.pitch + (3 * sx - cur.bo);
-                    const unsigned* w0 = reinterpret_cast<const unsigned*>(buf + (addr & ~3));
-                    const unsigned* w1 = reinterpret_cast<const unsigned*>(buf + ((addr + cur.pitch) & ~3));
-                    const unsigned shf = (addr & 3) * 8;
-                    const unsigned a0 = w0[0], a1 = w0[1], a2 = w0[2];
-                    const unsigned b0 = w1[0], b1 = w1[1], b2 = w1[2];
-                    p0lo = __funnelshift_r(a0, a1, shf); p0hi = __funnelshift_r(a1, a2, shf);
-                    p1lo = __funnelshift_r(b0, b1, shf); p1hi = __funnelshift_r(b1, b2, shf);
-                } else {
-                    const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
-                    const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
-                    p0lo = t00 | (t01 << 24); p0hi = t01 >> 8;
-                    p1lo = t10 | (t11 << 24); p1hi = t11 >> 8;
-                }
-                // (B0,B1,G0,G1) and (R0,R1) byte pairs for the two 16-bit x 8-bit dot products
-                const unsigned bg0 = __byte_perm(p0lo, p0hi, 0x4130), rr0 = __byte_perm(p0lo, p0hi, 0x0052);
-                const unsigned bg1 = __byte_perm(p1lo, p1hi, 0x4130), rr1 = __byte_perm(p1lo, p1hi, 0x0052);
-                // weights: w00=(32-fx)(32-fy)*32, w01=fx(32-fy)*32, w10=(32-fx)fy*32, w11=fx*fy*32
-                const unsigned P = fx * 0xFFFFu + 32u;          // (32-fx) | fx<<16
-                const unsigned W0 = ((32u - fy) * P) << 5;      // w00 | w01<<16
-                const unsigned W1 = (fy * P) << 5;              // w10 | w11<<16
-                unsigned accB = __dp2a_lo(W0, bg0, 16384u); accB = __dp2a_lo(W1, bg1, accB);
-                unsigned accG = __dp2a_hi(W0, bg0, 16384u); accG = __dp2a_hi(W1, bg1, accG);
-                unsigned accR = __dp2a_lo(W0, rr0, 16384u); accR = __dp2a_lo(W1, rr1, accR);
-                vB[j] = accB >> 15; vG[j] = accG >> 15; vR[j] = accR >> 15;
-            }
-            // ---- normalise through the table, BGR->RGB planes, 8-byte stores ----
-            const size_t o = (size_t)y * kOut + xs;
-            uint2 r, g, b;
-            r.x = (unsigned)lut[vR[0]] | ((unsigned)lut[vR[1]] << 16);
-            r.y = (unsigned)lut[vR[2]] | ((unsigned)lut[vR[3]] << 16);
-            g.x = (unsigned)lut[vG[0]] | ((unsigned)lut[vG[1]] << 16);
-            g.y = (unsigned)lut[vG[2]] | ((unsigned)lut[vG[3]] << 16);
-            b.x = (unsigned)lut[vB[0]] | ((unsigned)lut[vB[1]] << 16);
-            b.y = (unsigned)lut[vB[2]] | ((unsigned)lut[vB[3]] << 16);
-            *reinterpret_cast<uint2*>(oblob + o) = r;
-            *reinterpret_cast<uint2*>(oblob + (size_t)kOut * kOut + o) = g;
-            *reinterpret_cast<uint2*>(oblob + (size_t)2 * kOut * kOut + o) = b;
-            if (oal) {
-                uint8_t* p = oal + o * 3;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    p[3 * j] = (uint8_t)vB[j]; p[3 * j + 1] = (uint8_t)vG[j]; p[3 * j + 2] = (uint8_t)vR[j];
-                }
-            }
-            __syncwarp();
-            cur = nxt;
+        // 16x16 tiles when their source footprint fits the largest box, else 16x8
+        const double ax = fabs(iM[0]), ay = fabs(iM[1]), bx = fabs(iM[3]), by = fabs(iM[4]);
+        const bool big = 3.0 * (16.0 * ax + 16.0 * ay + 4.0) + 15.0 <= (double)kMaxBoxW &&
+                         (16.0 * bx + 16.0 * by + 4.0) <= (double)kMaxBoxH;
+        if (big) {
+            const int nt = kTilesX * (kOut / 16);   // 49
+            run_tiles<16>(a, maps, frame, fi, tab, buf_saddr0, bars, parity, half * nt / 2, (half + 1) * nt / 2,
+                          lane, lut, oblob, oal);
+        } else {
+            const int nt = kTilesX * (kOut / 8);    // 98
+            run_tiles<8>(a, maps, frame, fi, tab, buf_saddr0, bars, parity, half * nt / 2, (half + 1) * nt / 2,
+                         lane, lut, oblob, oal);
         }
     }
 }
@@ -315,6 +377,30 @@ __global__ void estimate_norm_kernel(const float* __restrict__ lmk, int n, doubl
     double m[6];
     estimate_norm_dev(lm, m);
     for (int j = 0; j < 6; ++j) M[(size_t)i * 6 + j] = m[j];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// u8 tensor [F][H][3W bytes] with pitches (stride, frame_bytes); one map per box size
+bool encode_frame_maps(TmapSet* set, const uint8_t* frames, int F, int H, int W, size_t stride,
+                       size_t frame_bytes) {
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tensormap_encode_fn());
+    if (!fn) return false;
+    if (((uintptr_t)frames & 15) || (stride & 15) || (frame_bytes & 15)) return false;
+    cuuint64_t gdim[3] = {(cuuint64_t)3 * W, (cuuint64_t)H, (cuuint64_t)F};
+    cuuint64_t gstr[2] = {(cuuint64_t)stride, (cuuint64_t)frame_bytes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    for (int hi = 0; hi < kNumH; ++hi)
+        for (int wi = 0; wi < kNumW; ++wi) {
+            cuuint32_t box[3] = {(cuuint32_t)kHostBoxW[wi], (cuuint32_t)kHostBoxH[hi], 1};
+            CUresult r = fn(&set->m[hi * kNumW + wi], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(frames),
+                            gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return false;
+        }
+    return true;
 }
 
 std::atomic<int> g_align_profile{0};
@@ -350,8 +436,10 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     a.out_blob = reinterpret_cast<__half*>(out_blob);
     a.out_aligned = out_aligned;
     a.counter = counter;
-    a.aligned16 = (((uintptr_t)frames & 15) == 0 && (stride & 15) == 0 && (a.frame_bytes & 15) == 0) ? 1 : 0;
-    const size_t smem = (size_t)kWarps * kWarpSmem;
+    TmapSet maps;
+    memset(&maps, 0, sizeof(maps));
+    a.use_tma = encode_frame_maps(&maps, frames, F, H, W, stride, a.frame_bytes) ? 1 : 0;
+    const size_t smem = (size_t)kWarps * kWarpSmem + 128;
     static thread_local bool configured = false;
     if (!configured) {
         FRP_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,7 +452,7 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
         if (!t_align_ev[0]) { cudaEventCreate(&t_align_ev[0]); cudaEventCreate(&t_align_ev[1]); }
         cudaEventRecord(t_align_ev[0], st);
     }
-    align_kernel<<<grid, kWarps * 32, smem, st>>>(a);
+    align_kernel<<<grid, kWarps * 32, smem, st>>>(maps, a);
     FRP_CHECK_LAUNCH();
     if (prof) { cudaEventRecord(t_align_ev[1], st); t_align_valid = true; }
     FRP_CUDA(cudaFreeAsync(counter, st));
@@ -419,7 +507,7 @@ int frp_align(int device, const uint8_t* frames, int F, int H, int W, size_t str
     int rc = frp_device_count(&ndev);
     if (rc) return rc;
     DeviceGuard dg(device);
-    // device copies keep a 16-byte aligned pitch so the staged path is always taken
+    // device copies keep a 16-byte aligned pitch so the TMA-staged path is always taken
     const size_t dstride = (stride + 15) & ~(size_t)15;
     uint8_t* d_frames = nullptr; int32_t* d_fi = nullptr; float* d_lmk = nullptr; double* d_M = nullptr;
     __half* d_blob = nullptr; uint8_t* d_al = nullptr;

@@ -109,6 +109,9 @@ int gemm_num_lists(const frp_gallery* g, int B);
 int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP,
                       uint64_t* cand, int nlists, cudaStream_t st);
 
+// cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (no libcuda link); null if unavailable
+void* tensormap_encode_fn();
+
 // exact fp64 re-rank of the survivors + certificate + output
 int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, int B, int k, int KP,
                   int flags, double tau, const uint64_t* cand, int nlists, int64_t* out_idx,

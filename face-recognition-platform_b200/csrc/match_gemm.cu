@@ -330,6 +330,8 @@ int pick_stages(int nkb) {
 
 }  // namespace
 
+void* tensormap_encode_fn() { return reinterpret_cast<void*>(get_encode_fn()); }
+
 bool gemm_supported(const frp_gallery* g) {
     return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
            get_encode_fn() != nullptr;
