@@ -23,6 +23,8 @@
 //            256-column accumulator stages.
 // Output contract is the scan kernel's: cand[B][nlists][KP] u64 keys.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -115,10 +117,36 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
-template <int KP, bool IS_L2>
+// ---- thread-block cluster helpers (CS = 2: the two query groups that stream the same
+// gallery tiles form a cluster; each CTA fetches half of every tile from L2 and
+// multicasts it into both CTAs' shared memory, halving the L2 -> SM traffic) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+
+template <int KP, bool IS_L2, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
-                  const GemmArgs a) {
+                  const __grid_constant__ CUtensorMap tmap_gh, const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B operands
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -139,7 +167,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_g);
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        prefetch_tmap(&tmap_gh);
+        // a smem slot is free when the MMAs of EVERY CTA of the cluster have retired (the
+        // peer multicasts into this CTA's slot too)
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         mbar_init(afull_bar, 1);
         mbar_fence_init();
@@ -147,8 +178,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();      // peer barriers are initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -165,7 +198,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (lane == 0) {
                     mbar_expect_tx(&full_bar[s], kBStageBytes);
-                    tma_load_2d(&tmap_g, &full_bar[s], smem_b + (size_t)s * kBStageBytes, kb * kBlockK, row0);
+                    if (CS > 1) {
+                        // this CTA's half of the tile (128 rows), delivered to both CTAs
+                        tma_load_2d_mc(&tmap_gh, &full_bar[s],
+                                       smem_b + (size_t)s * kBStageBytes + (size_t)crank * (kBStageBytes / 2),
+                                       kb * kBlockK, row0 + (int)crank * (kTileN / 2), (uint16_t)0x3);
+                    } else {
+                        tma_load_2d(&tmap_g, &full_bar[s], smem_b + (size_t)s * kBStageBytes, kb * kBlockK, row0);
+                    }
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -195,7 +235,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                         const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
                         umma_f16(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);                  // frees the smem slot when the MMAs retire
+                    // frees the smem slot (in every CTA of the cluster) when the MMAs retire
+                    if (CS > 1) umma_commit_mc(&empty_bar[s], (uint16_t)0x3);
+                    else umma_commit(&empty_bar[s]);
                     if (kb == a.nkb - 1) umma_commit(&tfull_bar[as]);   // accumulator ready
                 }
                 __syncwarp();
@@ -281,6 +323,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    // no CTA of the cluster may exit while its peer can still multicast data or barrier
+    // arrivals into its shared memory
+    if (CS > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -332,6 +377,12 @@ int pick_stages(int nkb) {
 
 void* tensormap_encode_fn() { return reinterpret_cast<void*>(get_encode_fn()); }
 
+// FRP_GEMM_NO_CLUSTER=1 disables the 2-CTA multicast variant (A/B measurements)
+static const bool g_gemm_no_cluster = []() {
+    const char* e = getenv("FRP_GEMM_NO_CLUSTER");
+    return e && e[0] == '1';
+}();
+
 bool gemm_supported(const frp_gallery* g) {
     return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
            get_encode_fn() != nullptr;
@@ -354,11 +405,15 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     const int nkb = g->dimp / kBlockK;
     const int stages = pick_stages(nkb);
     if (stages < 2) { set_error("match_gemm: not enough shared memory for dimp=%d", g->dimp); return FRP_E_UNSUPPORTED; }
-    CUtensorMap tq, tg;
+    CUtensorMap tq, tg, tgh;
     int rc = encode_map(&tq, q16, (uint64_t)groups * kTileM, g->dimp, kTileM);
     if (rc) return rc;
     rc = encode_map(&tg, g->g16, g->rows, g->dimp, kTileN);
     if (rc) return rc;
+    rc = encode_map(&tgh, g->g16, g->rows, g->dimp, kTileN / 2);   // half tiles for the cluster multicast
+    if (rc) return rc;
+    // an even number of 128-query groups runs as clusters of two CTAs sharing every gallery tile
+    const int cs = (groups % 2 == 0 && !g_gemm_no_cluster) ? 2 : 1;
     GemmArgs a;
     a.alive = g->alive;
     a.norm2 = g->norm2;
@@ -372,23 +427,49 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     a.metric = g->metric;
     const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256;
     dim3 grid(nlists, groups);
-#define FRP_GEMM_LAUNCH(KP_, L2_)                                                                        \
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)cs;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaSuccess;
+#define FRP_GEMM_LAUNCH(KP_, L2_, CS_)                                                                   \
     {                                                                                                    \
         static thread_local size_t configured = 0;                                                       \
         if (configured < smem) {                                                                         \
-            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_>,                                   \
+            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_, CS_>,                              \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
             configured = smem;                                                                           \
         }                                                                                                \
-        match_gemm_kernel<KP_, L2_><<<grid, kThreads, smem, st>>>(tq, tg, a);                            \
+        le = cudaLaunchKernelEx(&cfg, match_gemm_kernel<KP_, L2_, CS_>, tq, tg, tgh, a);                 \
     }
     const bool l2 = (g->metric == FRP_METRIC_L2);
-    if (KP == 16 && !l2) FRP_GEMM_LAUNCH(16, false)
-    else if (KP == 16 && l2) FRP_GEMM_LAUNCH(16, true)
-    else if (KP == 32 && !l2) FRP_GEMM_LAUNCH(32, false)
-    else if (KP == 32 && l2) FRP_GEMM_LAUNCH(32, true)
-    else { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
+    const int key = (KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (cs == 2 ? 1 : 0);
+    if (KP != 16 && KP != 32) { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
+    switch (key) {
+        case 0: FRP_GEMM_LAUNCH(16, false, 1) break;
+        case 1: FRP_GEMM_LAUNCH(16, false, 2) break;
+        case 2: FRP_GEMM_LAUNCH(16, true, 1) break;
+        case 3: FRP_GEMM_LAUNCH(16, true, 2) break;
+        case 4: FRP_GEMM_LAUNCH(32, false, 1) break;
+        case 5: FRP_GEMM_LAUNCH(32, false, 2) break;
+        case 6: FRP_GEMM_LAUNCH(32, true, 1) break;
+        default: FRP_GEMM_LAUNCH(32, true, 2) break;
+    }
 #undef FRP_GEMM_LAUNCH
+    if (le != cudaSuccess) {
+        set_error("match_gemm launch failed: %s", cudaGetErrorString(le));
+        cudaGetLastError();
+        return FRP_E_CUDA;
+    }
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }
