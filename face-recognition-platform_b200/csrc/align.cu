@@ -258,6 +258,74 @@ __device__ __forceinline__ void blend_tile(const AlignArgs& a, const uint8_t* fr
     }
 }
 
+// (v - 127.5) * float(1/127.5) -> fp16 without a table: float(v) by the 2^23 trick, then
+// ONE fused multiply-add; fp16(fma(v, c, -1)) == fp16((v - 127.5) * c) for all 256 values
+// (checked exhaustively in tests/test_oracle_cpu.py::test_norm_fma_form_matches_cv2)
+__device__ __forceinline__ unsigned short norm_half(unsigned v) {
+    const float f = __uint_as_float(0x4B000000u | v) - 8388608.0f;
+    const float n = __fmaf_rn(f, (float)(1.0 / 127.5), -1.0f);
+    return __half_as_ushort(__float2half_rn(n));
+}
+
+// one output tile, x-major lane mapping: lane -> column x0 + (lane & 15) and rows
+// y0 + 2j + (lane >> 4).  A warp-wide tap load then walks along ONE (rotated) source line
+// per half-warp, which keeps shared-memory bank conflicts at <= ~2-way for any staged row
+// pitch (the row-major mapping measured 4.7 wavefronts per load).
+template <int TH>
+__device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* frame, const int* tab,
+                                             const TileMeta& tm, uint32_t buf_saddr, int x0, int y0, int lane,
+                                             __half* oblob, uint8_t* oal) {
+    constexpr int NJ = TH / 2;
+    const int x = x0 + (lane & 15);
+    const int yb = y0 + (lane >> 4);
+    const int ad = tab[x], bd = tab[kOut + x];
+    unsigned short* o16 = reinterpret_cast<unsigned short*>(oblob) + (size_t)yb * kOut + x;
+    uint8_t* o8 = oal ? oal + ((size_t)yb * kOut + x) * 3 : nullptr;
+    const int base = -tm.sy0 * tm.pitch - tm.c0;
+    unsigned vB[NJ], vG[NJ], vR[NJ];
+    if (!tm.direct) {      // warp-uniform: one branch per tile, not per pixel
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int y = yb + 2 * j;
+            const int X = (tab[2 * kOut + y] + ad) >> 5, Y = (tab[3 * kOut + y] + bd) >> 5;
+            const int off = (Y >> 5) * tm.pitch + 3 * (X >> 5) + base;
+            const uint32_t w0 = buf_saddr + (off & ~3);
+            const uint32_t w1 = w0 + tm.pitch;
+            const unsigned shf = (off & 3) * 8;
+            const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32(w0 + 8);
+            const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32(w1 + 8);
+            blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
+                     __funnelshift_r(b1, b2, shf), X & 31, Y & 31, vB[j], vG[j], vR[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int y = yb + 2 * j;
+            const int X = (tab[2 * kOut + y] + ad) >> 5, Y = (tab[3 * kOut + y] + bd) >> 5;
+            const int sx = max(-32768, min(32767, X >> 5));
+            const int sy = max(-32768, min(32767, Y >> 5));
+            const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
+            const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
+            blend_px(t00 | (t01 << 24), t01 >> 8, t10 | (t11 << 24), t11 >> 8, X & 31, Y & 31, vB[j], vG[j],
+                     vR[j]);
+        }
+    }
+    // BGR -> RGB planes; a half-warp writes 16 consecutive halfs (one 32-byte sector)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        o16[(size_t)j * 2 * kOut] = norm_half(vR[j]);
+        o16[(size_t)kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vG[j]);
+        o16[(size_t)2 * kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vB[j]);
+    }
+    if (o8) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            uint8_t* p = o8 + (size_t)j * 2 * kOut * 3;
+            p[0] = (uint8_t)vB[j]; p[1] = (uint8_t)vG[j]; p[2] = (uint8_t)vR[j];
+        }
+    }
+}
+
 // all tiles [t_begin, t_end) of one crop with tile height TH, double buffered
 template <int TH>
 __device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& maps, const uint8_t* frame, int fi,
@@ -279,8 +347,8 @@ __device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& map
             mbar_wait(&bars[b], (parity >> b) & 1u);
             parity ^= (1u << b);
         }
-        blend_tile<TH>(a, frame, tab, cur, buf_saddr0 + (uint32_t)(b * kBufBytes), (t % kTilesX) * kTileW,
-                       (t / kTilesX) * TH, lane, lut, oblob, oal);
+        blend_tile_x<TH>(a, frame, tab, cur, buf_saddr0 + (uint32_t)(b * kBufBytes), (t % kTilesX) * kTileW,
+                         (t / kTilesX) * TH, lane, oblob, oal);
         __syncwarp();      // every lane is done with buffer b before it is refilled
         cur = nxt;
     }

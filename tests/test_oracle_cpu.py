@@ -114,6 +114,16 @@ def test_norm_lut_matches_cv2_golden(golden_align):
     assert np.array_equal(lut.astype(np.float16), golden_align["lut_f16"])
 
 
+def test_norm_fma_form_matches_cv2(golden_align):
+    """The kernel normalises with ONE fused multiply-add, fp16(fma(v, f32(1/127.5), -1));
+    exhaustively equal to cv2.dnn.blobFromImages' (v - 127.5) * f32(1/127.5) after the
+    fp16 cast."""
+    v = np.arange(256, dtype=np.float64)
+    c = np.float64(np.float32(1.0 / 127.5))
+    fma = (v * c - 1.0).astype(np.float32).astype(np.float16)     # exact product, one rounding
+    assert np.array_equal(fma, golden_align["lut_f16"])
+
+
 @pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
 def test_live_reference_agrees_with_np_oracle():
     fs, ENC, _ = ref_loader.load_reference()
