@@ -128,14 +128,12 @@ template <int TH>
 __device__ __forceinline__ TileMeta stage_tile(const AlignArgs& a, const TmapSet& maps, const int* tab, int x0,
                                                int y0, int frame_index, uint32_t buf_saddr, uint64_t* bar,
                                                int lane) {
-    const int* adelta = tab;
-    const int* bdelta = tab + kOut;
-    const int* X0 = tab + 2 * kOut;
-    const int* Y0 = tab + 3 * kOut;
-    const int xa = adelta[x0], xb = adelta[x0 + kTileW - 1];
-    const int ya = bdelta[x0], yb = bdelta[x0 + kTileW - 1];
-    const int Xa = X0[y0], Xb = X0[y0 + TH - 1];
-    const int Ya = Y0[y0], Yb = Y0[y0 + TH - 1];
+    // tables: adelta | bdelta | X0 | Y0, read with shared-space loads
+    const uint32_t ts = smem_u32(tab);
+    const int xa = (int)lds32(ts + 4 * x0), xb = (int)lds32(ts + 4 * (x0 + kTileW - 1));
+    const int ya = (int)lds32(ts + 4 * (kOut + x0)), yb = (int)lds32(ts + 4 * (kOut + x0 + kTileW - 1));
+    const int Xa = (int)lds32(ts + 4 * (2 * kOut + y0)), Xb = (int)lds32(ts + 4 * (2 * kOut + y0 + TH - 1));
+    const int Ya = (int)lds32(ts + 4 * (3 * kOut + y0)), Yb = (int)lds32(ts + 4 * (3 * kOut + y0 + TH - 1));
     const int sx_min = (min(Xa, Xb) + min(xa, xb)) >> 10;
     const int sx_max = (max(Xa, Xb) + max(xa, xb)) >> 10;
     const int sy_min = (min(Ya, Yb) + min(ya, yb)) >> 10;
@@ -278,7 +276,9 @@ __device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* 
     constexpr int NJ = TH / 2;
     const int x = x0 + (lane & 15);
     const int yb = y0 + (lane >> 4);
-    const int ad = tab[x], bd = tab[kOut + x];
+    const uint32_t ts = smem_u32(tab);
+    const int ad = (int)lds32(ts + 4 * x), bd = (int)lds32(ts + 4 * (kOut + x));
+    const uint32_t tsy = ts + 4 * (2 * kOut + yb);     // X0[yb]; Y0 is kOut ints further
     unsigned short* o16 = reinterpret_cast<unsigned short*>(oblob) + (size_t)yb * kOut + x;
     uint8_t* o8 = oal ? oal + ((size_t)yb * kOut + x) * 3 : nullptr;
     const int base = -tm.sy0 * tm.pitch - tm.c0;
@@ -287,7 +287,7 @@ __device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int y = yb + 2 * j;
-            const int X = (tab[2 * kOut + y] + ad) >> 5, Y = (tab[3 * kOut + y] + bd) >> 5;
+            const int X = ((int)lds32(tsy + 8 * j) + ad) >> 5, Y = ((int)lds32(tsy + 8 * j + 4 * kOut) + bd) >> 5;
             const int off = (Y >> 5) * tm.pitch + 3 * (X >> 5) + base;
             const uint32_t w0 = buf_saddr + (off & ~3);
             const uint32_t w1 = w0 + tm.pitch;
@@ -301,7 +301,7 @@ __device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int y = yb + 2 * j;
-            const int X = (tab[2 * kOut + y] + ad) >> 5, Y = (tab[3 * kOut + y] + bd) >> 5;
+            const int X = ((int)lds32(tsy + 8 * j) + ad) >> 5, Y = ((int)lds32(tsy + 8 * j + 4 * kOut) + bd) >> 5;
             const int sx = max(-32768, min(32767, X >> 5));
             const int sy = max(-32768, min(32767, Y >> 5));
             const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);

@@ -176,6 +176,40 @@ def test_store_delete_mirror_dict_semantics():
     assert any("dup" in v and "id0000040" in v for v in cl.values())
 
 
+def test_camera_scan_batched_front_end():
+    """scan_cameras == the reference's per-face loop of routes/camera.py:243-259 restated
+    on the oracle: every gallery row with match and distance <= confidence_threshold."""
+    rng = np.random.default_rng(21)
+    G = rng.normal(0, 0.05, (600, 128))
+    G[300:380] = G[5] + rng.normal(0, 0.004, (80, 128))       # > 64 matches for one face -> dense path
+    fs, enc = _service_from(G)
+    ref = {"id%07d" % i: g.tolist() for i, g in enumerate(G)}
+    faces = {
+        "cam0": [G[10] + rng.normal(0, 0.02, 128), rng.normal(0, 0.05, 128)],
+        7: [G[5] + rng.normal(0, 0.003, 128)],
+        "cam2": [],
+        "cam3": [G[i] + rng.normal(0, 0.02, 128) for i in range(20, 34)],      # 14 faces, max_faces 10
+    }
+    cfg = {"cam0": {"confidence_threshold": 0.5}, "cam3": {"confidence_threshold": 0.25}}
+    got = frp_b200.scan_cameras(fs, faces, cfg)
+    assert list(got.keys()) == list(faces.keys())
+    for cam, fl in faces.items():
+        thr = cfg.get(cam, {}).get("confidence_threshold", 0.6)
+        want = []
+        for f in list(fl)[:10]:
+            for m in o.compare_faces(ref, f, 0.6):
+                if m["match"] and m["distance"] <= thr:
+                    want.append({"camera_id": cam, "target": m["target"], "distance": m["distance"],
+                                 "confidence": m["confidence"]})
+        assert [w["target"] for w in want] == [r["target"] for r in got[cam]], cam
+        assert [w["confidence"] for w in want] == [r["confidence"] for r in got[cam]]
+        assert all(r["camera_id"] == cam for r in got[cam])
+        if want:
+            assert max(abs(w["distance"] - r["distance"]) for w, r in zip(want, got[cam])) < TIGHT
+    assert len(got[7]) > 64 and got["cam2"] == []
+    assert frp_b200.scan_cameras(FaceService(GalleryDict(), raise_errors=True), faces) == {c: [] for c in faces}
+
+
 # ----------------------------------------------------------------------------
 # cosine 512-d (insightface semantics; oracle = numpy restatement)
 # ----------------------------------------------------------------------------
