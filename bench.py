@@ -519,6 +519,39 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     except Exception as e:  # pragma: no cover
         out["align"]["cpu_baseline"] = {"error": str(e)}
 
+    # config C1: face_recognition compare_faces, 1 query vs 1k synthetic 128-d encodings,
+    # tolerance 0.6, through the drop-in FaceService (all 1 000 result dicts, like the reference)
+    try:
+        G1 = o.synth_l2_gallery(1000, 128, seed=1234)
+        Q1, _ = o.synth_l2_queries(G1, 64, seed=4321)
+        enc = frp.GalleryDict()
+        enc.bulk_load(["id%07d" % i for i in range(len(G1))], G1)
+        fs = frp.FaceService(enc, tolerance=0.6, raise_errors=True)
+        ref = {"id%07d" % i: g.tolist() for i, g in enumerate(G1)}
+        for q in Q1[:4]:
+            fs.compare_faces(q)
+        t0 = time.perf_counter()
+        for q in Q1:
+            fs.compare_faces(q)
+        t_gpu = (time.perf_counter() - t0) / len(Q1)
+        t0 = time.perf_counter()
+        for q in Q1:
+            fs.match_topk(q[None], 0.6, 5)
+        t_topk = (time.perf_counter() - t0) / len(Q1)
+        t0 = time.perf_counter()
+        for q in Q1[:16]:
+            o.compare_faces(ref, q, 0.6)
+        t_cpu = (time.perf_counter() - t0) / 16
+        out["c1_compare_faces"] = {
+            "workload": "1 query vs 1 000 x 128-d, tolerance 0.6 (BASELINE configs[0])",
+            "drop_in_compare_faces_ms": t_gpu * 1e3, "drop_in_queries_per_s": 1.0 / t_gpu,
+            "match_topk_ms": t_topk * 1e3, "match_topk_queries_per_s": 1.0 / t_topk,
+            "cpu_port_compare_faces_ms": t_cpu * 1e3, "cpu_port_queries_per_s": 1.0 / t_cpu,
+            "note": "compare_faces returns all 1 000 dicts (O(N) Python by contract, face_service.py:414-429); "
+                    "match_topk is threshold-then-top-5 on the device"}
+    except Exception as e:  # pragma: no cover
+        out["c1_compare_faces"] = {"error": str(e)}
+
     # config C5: 32 synthetic 1080p streams per tick, ~8 faces each -> align -> (backbone out
     # of scope: synthetic 512-d embeddings) -> match vs the resident gallery
     try:

@@ -12,11 +12,13 @@
 // bytes x rows x frame, zero-filled outside the frame, which IS BORDER_CONSTANT 0 —
 // into the warp's private shared-memory buffer, double buffered against the blend of
 // the previous tile through two mbarriers.  Box sizes come from a 5x5 ladder of tensor
-// maps so small faces do not over-fetch.  Each lane then produces TH/2 consecutive
-// output pixels from shared memory with integer dp2a blends (bit-exact with cv2),
-// maps them through a 256-entry fp16 table and writes 16-byte (8-byte) segments of the
-// three output planes.  Tiles whose footprint exceeds the largest box (or frames whose
-// pitch is not 16-byte aligned) are sampled tap by tap from global memory.
+// maps so small faces do not over-fetch (the inner TMA coordinate must be 16-byte
+// aligned, so boxes start at floor16(3*sx_min)).  Lanes are mapped x-major (16 columns x
+// 2 rows per warp instruction): each lane produces TH/2 output pixels from shared memory
+// with integer dp2a blends (bit-exact with cv2), normalises with one FFMA (exhaustively
+// equal to cv2's fp32 result after the fp16 cast) and a half-warp writes one 32-byte
+// sector of each output plane.  Tiles whose footprint exceeds the largest box (or frames
+// whose pitch is not 16-byte aligned) are sampled tap by tap from global memory.
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
@@ -182,80 +184,6 @@ __device__ __forceinline__ void blend_px(unsigned p0lo, unsigned p0hi, unsigned 
     vB = accB >> 15; vG = accG >> 15; vR = accR >> 15;
 }
 
-// one output tile: each lane produces PXL = TH/2 consecutive pixels of one output row
-template <int TH>
-__device__ __forceinline__ void blend_tile(const AlignArgs& a, const uint8_t* frame, const int* tab,
-                                           const TileMeta& tm, uint32_t buf_saddr, int x0, int y0, int lane,
-                                           const unsigned short* lut, __half* oblob, uint8_t* oal) {
-    constexpr int PXL = TH / 2;
-    constexpr int LPR = kTileW / PXL;               // lanes per output row
-    const int y = y0 + lane / LPR;
-    const int xs = x0 + (lane % LPR) * PXL;
-    const int Xy = tab[2 * kOut + y], Yy = tab[3 * kOut + y];
-    int adv[PXL], bdv[PXL];
-#pragma unroll
-    for (int j = 0; j < PXL; j += 4) {
-        const int4 ad = *reinterpret_cast<const int4*>(tab + xs + j);
-        const int4 bd = *reinterpret_cast<const int4*>(tab + kOut + xs + j);
-        adv[j] = ad.x; adv[j + 1] = ad.y; adv[j + 2] = ad.z; adv[j + 3] = ad.w;
-        bdv[j] = bd.x; bdv[j + 1] = bd.y; bdv[j + 2] = bd.z; bdv[j + 3] = bd.w;
-    }
-    unsigned vB[PXL], vG[PXL], vR[PXL];
-    if (!tm.direct) {
-        const int base = -tm.sy0 * tm.pitch - tm.c0;
-#pragma unroll
-        for (int j = 0; j < PXL; ++j) {
-            const int X = (Xy + adv[j]) >> 5, Y = (Yy + bdv[j]) >> 5;
-            const int sx = X >> 5, sy = Y >> 5;
-            const unsigned fx = X & 31, fy = Y & 31;
-            const int off = sy * tm.pitch + 3 * sx + base;
-            const uint32_t w0 = buf_saddr + (off & ~3);
-            const uint32_t w1 = w0 + tm.pitch;
-            const unsigned shf = (off & 3) * 8;
-            const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32(w0 + 8);
-            const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32(w1 + 8);
-            blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
-                     __funnelshift_r(b1, b2, shf), fx, fy, vB[j], vG[j], vR[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < PXL; ++j) {
-            const int X = (Xy + adv[j]) >> 5, Y = (Yy + bdv[j]) >> 5;
-            const int sx = max(-32768, min(32767, X >> 5));
-            const int sy = max(-32768, min(32767, Y >> 5));
-            const unsigned fx = X & 31, fy = Y & 31;
-            const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
-            const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
-            blend_px(t00 | (t01 << 24), t01 >> 8, t10 | (t11 << 24), t11 >> 8, fx, fy, vB[j], vG[j], vR[j]);
-        }
-    }
-    // ---- normalise through the table, BGR->RGB planes, vector stores ----
-    const size_t o = (size_t)y * kOut + xs;
-    unsigned r[PXL / 2], g[PXL / 2], b[PXL / 2];
-#pragma unroll
-    for (int j = 0; j < PXL / 2; ++j) {
-        r[j] = (unsigned)lut[vR[2 * j]] | ((unsigned)lut[vR[2 * j + 1]] << 16);
-        g[j] = (unsigned)lut[vG[2 * j]] | ((unsigned)lut[vG[2 * j + 1]] << 16);
-        b[j] = (unsigned)lut[vB[2 * j]] | ((unsigned)lut[vB[2 * j + 1]] << 16);
-    }
-    if (PXL == 8) {
-        *reinterpret_cast<uint4*>(oblob + o) = make_uint4(r[0], r[1], r[2], r[3]);
-        *reinterpret_cast<uint4*>(oblob + (size_t)kOut * kOut + o) = make_uint4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<uint4*>(oblob + (size_t)2 * kOut * kOut + o) = make_uint4(b[0], b[1], b[2], b[3]);
-    } else {
-        *reinterpret_cast<uint2*>(oblob + o) = make_uint2(r[0], r[1]);
-        *reinterpret_cast<uint2*>(oblob + (size_t)kOut * kOut + o) = make_uint2(g[0], g[1]);
-        *reinterpret_cast<uint2*>(oblob + (size_t)2 * kOut * kOut + o) = make_uint2(b[0], b[1]);
-    }
-    if (oal) {
-        uint8_t* p = oal + o * 3;
-#pragma unroll
-        for (int j = 0; j < PXL; ++j) {
-            p[3 * j] = (uint8_t)vB[j]; p[3 * j + 1] = (uint8_t)vG[j]; p[3 * j + 2] = (uint8_t)vR[j];
-        }
-    }
-}
-
 // (v - 127.5) * float(1/127.5) -> fp16 without a table: float(v) by the 2^23 trick, then
 // ONE fused multiply-add; fp16(fma(v, c, -1)) == fp16((v - 127.5) * c) for all 256 values
 // (checked exhaustively in tests/test_oracle_cpu.py::test_norm_fma_form_matches_cv2)
@@ -330,8 +258,7 @@ __device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* 
 template <int TH>
 __device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& maps, const uint8_t* frame, int fi,
                                           const int* tab, uint32_t buf_saddr0, uint64_t* bars, uint32_t& parity,
-                                          int t_begin, int t_end, int lane, const unsigned short* lut,
-                                          __half* oblob, uint8_t* oal) {
+                                          int t_begin, int t_end, int lane, __half* oblob, uint8_t* oal) {
     TileMeta cur, nxt;
     cur = stage_tile<TH>(a, maps, tab, (t_begin % kTilesX) * kTileW, (t_begin / kTilesX) * TH, fi, buf_saddr0,
                          &bars[0], lane);
@@ -357,13 +284,7 @@ __device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& map
 __global__ void __launch_bounds__(kWarps * 32, 1)
 align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __half s_lut[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // (v - 127.5) * float(1/127.5) in fp32, as cv2.dnn.blobFromImages computes it
-    if (threadIdx.x < 256) {
-        const float f = __fmul_rn(__fsub_rn((float)threadIdx.x, 127.5f), (float)(1.0 / 127.5));
-        s_lut[threadIdx.x] = __float2half_rn(f);
-    }
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t* wsm = smem + (size_t)warp * kWarpSmem;
     int* tab = reinterpret_cast<int*>(wsm);
@@ -375,7 +296,6 @@ align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
         mbar_fence_init();
     }
     __syncthreads();
-    const unsigned short* lut = reinterpret_cast<const unsigned short*>(s_lut);
     uint32_t parity = 0;
 
     const int nitems = a.n * kItemsPerCrop;
@@ -428,11 +348,11 @@ align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
         if (big) {
             const int nt = kTilesX * (kOut / 16);   // 49
             run_tiles<16>(a, maps, frame, fi, tab, buf_saddr0, bars, parity, half * nt / 2, (half + 1) * nt / 2,
-                          lane, lut, oblob, oal);
+                          lane, oblob, oal);
         } else {
             const int nt = kTilesX * (kOut / 8);    // 98
             run_tiles<8>(a, maps, frame, fi, tab, buf_saddr0, bars, parity, half * nt / 2, (half + 1) * nt / 2,
-                         lane, lut, oblob, oal);
+                         lane, oblob, oal);
         }
     }
 }
