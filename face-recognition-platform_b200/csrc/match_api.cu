@@ -172,7 +172,8 @@ int frp_match_device(frp_gallery_t* g, const float* queries_dev, int B, double t
     if (rc) return rc;
     std::shared_lock<std::shared_mutex> lk(g->mu);
     DeviceGuard dg(g->device);
-    return match_device_locked(g, queries_dev, B, tau, k, flags, pick_kp(k), out_idx_dev, out_score_dev,
+    return match_device_locked(g, queries_dev, B, tau, k, flags, (flags & FRP_MATCH_WIDE) ? 64 : pick_kp(k),
+                               out_idx_dev, out_score_dev,
                                out_count_dev, out_status_dev, (cudaStream_t)stream);
 }
 

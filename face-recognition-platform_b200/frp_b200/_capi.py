@@ -18,6 +18,7 @@ FRP_E_INVALID, FRP_E_CUDA, FRP_E_NODEVICE, FRP_E_NOMEM, FRP_E_IO, FRP_E_UNSUPPOR
 METRIC_L2, METRIC_COS = 0, 1
 MATCH_THRESHOLD, MATCH_NO_THRESHOLD, MATCH_FORCE_SCAN, MATCH_FORCE_GEMM, MATCH_FORCE_EXACT, MATCH_STRICT = \
     0x0, 0x1, 0x2, 0x4, 0x8, 0x10
+MATCH_WIDE = 0x20
 STATUS_OK, STATUS_FALLBACK, STATUS_UNCERTIFIED = 0, 1, 2
 
 

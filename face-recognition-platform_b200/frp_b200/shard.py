@@ -130,3 +130,22 @@ class ShardedMatcher:
         m = metric if metric is not None else self.g.metric
         self._merge(m, self.world, B, k, recv, out_idx, out_score, out_count, any_status, stream)
         return out_idx, out_score, out_count, any_status
+
+    def match_certified(self, q_dev, tau: float, k: int, flags: int = 0, metric: Optional[int] = None):
+        """``match`` plus the fallback ladder of the host API: if any shard could not
+        certify its fp16 prefilter (status word != 0 after the merge, identical on every
+        rank, so all ranks take the same branch), the step is repeated against the fp32
+        master and, if needed, with the widest candidate lists.  Costs one device->host
+        read of a 4-byte flag per step.  Returns (idx, score, count, level) with level
+        0 = certified by the fp16 path, 1/2 = certified by a fallback, 3 = uncertified
+        (more than 64 exact ties at the cut)."""
+        from ._capi import MATCH_FORCE_EXACT, MATCH_FORCE_GEMM, MATCH_FORCE_SCAN, MATCH_WIDE
+        out = self.match(q_dev, tau, k, flags, metric)
+        if int(out[3].item()) == 0:
+            return out[0], out[1], out[2], 0
+        base = flags & ~(MATCH_FORCE_GEMM | MATCH_FORCE_SCAN)
+        for level, extra in ((1, MATCH_FORCE_EXACT), (2, MATCH_FORCE_EXACT | MATCH_WIDE)):
+            out = self.match(q_dev, tau, k, base | extra, metric)
+            if int(out[3].item()) == 0:
+                return out[0], out[1], out[2], level
+        return out[0], out[1], out[2], 3

@@ -325,6 +325,36 @@ def test_dims_and_metrics(dim, metric):
     assert np.abs(gal.scores(Q) - S).max() < TIGHT
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_exact_ties_and_inclusive_threshold(seed):
+    """Lattice-valued encodings make distances tie EXACTLY (in fp16, fp32 and fp64 alike) and
+    put gallery rows exactly AT the tolerance: the inclusive `<=` of face_service.py:411 and
+    the stable tie order (dict insertion order, :431) must then be reproduced bit for bit,
+    on every path (scan / tcgen05 / fp32 master)."""
+    rng = np.random.default_rng(1000 + seed)
+    dim = int(rng.choice([64, 128, 512]))
+    N = int(rng.integers(1, 400))
+    B = int(rng.integers(1, 10))
+    k = int(rng.integers(1, 13))
+    G = rng.integers(-2, 3, (N, dim)).astype(np.float64) / 16.0
+    G[rng.integers(0, N, N // 3)] = G[rng.integers(0, N, N // 3)]          # exact duplicates
+    Q = rng.integers(-2, 3, (B, dim)).astype(np.float64) / 16.0
+    D = np.stack([np.linalg.norm(G - q, axis=1) for q in Q])               # exact sums, one sqrt
+    tau = float(np.sort(D[0])[min(N - 1, int(rng.integers(0, 2 * k + 1)))])  # a row sits exactly at tau
+    gal = Gallery(dim, METRIC_L2)
+    gal.append(G)
+    assert np.array_equal(gal.scores(Q), D)                                # dense dump bit-exact
+    for thresholded in (True, False):
+        widx, wd, wcnt = o.l2_match_topk(G, Q, tau, k, thresholded)
+        fl = 0 if thresholded else MATCH_NO_THRESHOLD
+        for path in (MATCH_FORCE_SCAN, MATCH_FORCE_GEMM, MATCH_FORCE_EXACT):
+            idx, sc, cnt, st = gal.match(Q, tau, k, fl | path)
+            assert np.array_equal(cnt, wcnt.astype(np.int32)), (path, thresholded)
+            assert np.array_equal(idx, widx), (path, thresholded)
+            assert np.array_equal(sc, wd.astype(np.float32), equal_nan=True)
+            assert np.all(st <= 1)
+
+
 # ----------------------------------------------------------------------------
 # edge cases
 # ----------------------------------------------------------------------------

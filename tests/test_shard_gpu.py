@@ -74,6 +74,21 @@ def test_result_is_independent_of_shard_count(metric):
             assert np.array_equal(idx, base[0]) and np.array_equal(sc, base[1], equal_nan=True)
 
 
+def test_match_certified_takes_the_fallback_ladder():
+    G = o.synth_cos_gallery(6000, 512, seed=7)
+    G[2000:2100] = G[3]                       # 101 identical rows: more ties than a candidate list holds
+    g = Gallery(512, METRIC_COS)
+    g.append(G)
+    m = ShardedMatcher(g, 6000, 0, 1)
+    q = torch.from_numpy(G[3:4].copy()).cuda()
+    idx, sc, cnt, level = m.match_certified(q, 0.9, 10)
+    torch.cuda.synchronize()
+    assert level in (1, 2)
+    assert idx.cpu().numpy()[0].tolist() == [3] + list(range(2000, 2009))
+    idx, sc, cnt, level = m.match_certified(torch.from_numpy(G[10:12].copy()).cuda(), 0.9, 10)
+    assert level == 0 and cnt.cpu().numpy().tolist() == [1, 1]
+
+
 def test_single_rank_sharded_matcher_runs_end_to_end():
     G = o.synth_cos_gallery(5000, 512, seed=5)
     Q, _ = o.synth_cos_queries(G, 4, seed=6)
