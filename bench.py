@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--tau", type=float, default=0.40)
     ap.add_argument("--no-extras", action="store_true", help="skip the align / batch-1 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default=os.environ.get("FRP_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
+                    help="multi-GPU merge: NCCL all-gather + merge kernel, or the fused peer-memory kernel")
     ap.add_argument("--also-batches", default="", help="comma list of extra batch sizes timed on the same gallery")
     return ap.parse_args()
 
@@ -245,7 +247,18 @@ def run_ours(args):
         if rank != 0:
             keep = torch.empty((4096, 512), device=device)
         dist.broadcast(keep, 0)
-    matcher = frp.ShardedMatcher(gal, args.rows, rank, world)
+    matcher = frp.ShardedMatcher(gal, args.rows, rank, world, exchange=args.exchange)
+    exchange_check = None
+    if args.exchange == "p2p" and world > 1:
+        # the fused peer-memory exchange must give exactly what all-gather + merge gives
+        ref_m = frp.ShardedMatcher(gal, args.rows, rank, world, exchange="nccl")
+        qchk = make_queries(torch, 1, B, keep, 4242, device)[0]
+        a_ = [x.clone() for x in matcher.match(qchk, tau, k)]
+        b_ = [x.clone() for x in ref_m.match(qchk, tau, k)]
+        torch.cuda.synchronize()
+        exchange_check = bool(torch.equal(a_[0], b_[0]) and torch.equal(a_[2], b_[2]) and
+                              torch.equal(torch.nan_to_num(a_[1]), torch.nan_to_num(b_[1])) and
+                              int(a_[3].item()) == int(b_[3].item()))
     nq = K + W
     queries = make_queries(torch, nq, B, keep, 99, device)
     stream = torch.cuda.current_stream().cuda_stream
@@ -424,6 +437,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f16 (fp32 accumulate; fp64 re-rank of fp32 master)", "data": "synthetic",
                 "config": config(args, world), "match_path": path, "gpu_launches": int(launches),
+                "exchange": args.exchange if world > 1 else "none", "exchange_equals_nccl": exchange_check,
                 "uncertified_last_step": fallback_steps, "clocks": clocks, "e2e": e2e, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu

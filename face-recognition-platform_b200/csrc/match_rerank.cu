@@ -348,6 +348,129 @@ __global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t
     if (tid == 0) out_count[b] = cnt;
 }
 
+// ---------------------------------------------------------------------------
+// fused exchange + merge over peer memory (NVLink / NVSwitch), no NCCL call:
+//   phase 1  every block copies a slice of this rank's packed record straight into
+//            slot [epoch&1][rank] of EVERY rank's exchange buffer (peer stores);
+//            the last block to finish publishes flag[epoch&1][rank] = epoch on every
+//            rank (st.release.sys after __threadfence_system)
+//   phase 2  the blocks wait (ld.acquire.sys) until all R flags of THIS rank's buffer
+//            carry the epoch, then merge the R records like merge_topk_kernel.
+// Exchange buffer of a rank: [0,256) u32 flag[2][32]; then recv[2][R][rec_bytes].
+// Double buffering by epoch parity is sufficient: a rank can only publish epoch e+1
+// after its own merge of epoch e has completed (stream order), so slot parity e&1 is
+// never overwritten while a peer still reads it.
+// ---------------------------------------------------------------------------
+constexpr int kExchHeader = 256;
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __restrict__ send,
+                  uint8_t* const* __restrict__ peers, size_t rec_bytes, uint32_t epoch,
+                  unsigned int* __restrict__ block_counter, int64_t* __restrict__ out_idx,
+                  float* __restrict__ out_score, int32_t* __restrict__ out_count,
+                  int32_t* __restrict__ out_any_status) {
+    __shared__ int64_t s_idx[kMergeMax];
+    __shared__ float s_sc[kMergeMax];
+    __shared__ int s_n;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const uint32_t par = epoch & 1u;
+
+    // ---- phase 1: push ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(send);
+        const size_t nvec = rec_bytes / 16;
+        const size_t total = nvec * (size_t)R;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const int r = (int)(i / nvec);
+            const size_t v = i % nvec;
+            uint4* dst = reinterpret_cast<uint4*>(peers[r] + kExchHeader + ((size_t)par * R + rank) * rec_bytes);
+            dst[v] = src[v];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(block_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (tid < R) st_release_sys(reinterpret_cast<uint32_t*>(peers[tid]) + par * 32 + rank, epoch);
+        if (tid == 0) *block_counter = 0u;     // ready for the next launch
+    }
+
+    // ---- phase 2: wait for every rank's record in this rank's buffer ----
+    const uint8_t* mine = peers[rank];
+    if (tid < R) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine) + par * 32 + tid;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != epoch) {
+            if (clock64() - t0 > 6000000000ll) {      // ~3 s: a peer died; flag the result, do not hang
+                if (out_any_status) atomicOr(out_any_status, 0x100);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+
+    // ---- merge ----
+    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 4, o3 = o2 + (size_t)B * 4;
+    const uint8_t* recv = mine + kExchHeader + (size_t)par * R * rec_bytes;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        const int total = R * k;
+        for (int e = tid; e < total; e += blockDim.x) {
+            const int r = e / k, j = e % k;
+            const uint8_t* rec = recv + (size_t)r * rec_bytes;
+            const int32_t* cnt = reinterpret_cast<const int32_t*>(rec + o2);
+            if (j < cnt[b]) {
+                const int pos = atomicAdd(&s_n, 1);
+                s_idx[pos] = reinterpret_cast<const int64_t*>(rec)[(size_t)b * k + j];
+                s_sc[pos] = reinterpret_cast<const float*>(rec + o1)[(size_t)b * k + j];
+            }
+        }
+        if (out_any_status && tid < R) {
+            const int32_t* stt = reinterpret_cast<const int32_t*>(recv + (size_t)tid * rec_bytes + o3);
+            if (stt[b] != 0) atomicOr(out_any_status, 1);
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int e = tid; e < n; e += blockDim.x) {
+            const float v = s_sc[e];
+            const int64_t id = s_idx[e];
+            int rk = 0;
+            for (int c = 0; c < n; ++c) {
+                const float vc = s_sc[c];
+                const int64_t ic = s_idx[c];
+                const bool bt = (metric == FRP_METRIC_COS) ? (vc > v || (vc == v && ic < id))
+                                                           : (vc < v || (vc == v && ic < id));
+                if (bt) ++rk;
+            }
+            if (rk < k) {
+                out_idx[(size_t)b * k + rk] = id;
+                out_score[(size_t)b * k + rk] = v;
+            }
+        }
+        const int cntb = n < k ? n : k;
+        for (int i = cntb + tid; i < k; i += blockDim.x) {
+            out_idx[(size_t)b * k + i] = -1;
+            out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+        }
+        if (tid == 0) out_count[b] = cntb;
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
@@ -411,6 +534,36 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
 }  // namespace frp
 
 extern "C" {
+
+size_t frp_exchange_buffer_bytes(int R, int B, int k) {
+    size_t rec = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
+    rec = (rec + 15) / 16 * 16;
+    return (size_t)frp::kExchHeader + 2 * (size_t)R * rec;
+}
+
+int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void* send_record,
+                          void* const* peers_dev, uint32_t epoch, unsigned int* counter_dev,
+                          int64_t* out_idx, float* out_score, int32_t* out_count,
+                          int32_t* out_any_status, void* stream) {
+    using namespace frp;
+    if (R <= 0 || R > 32 || rank < 0 || rank >= R || B <= 0 || k <= 0 || R * k > kMergeMax || !send_record ||
+        !peers_dev || !counter_dev || !out_idx || !out_score || !out_count) {
+        set_error("frp_push_merge_device: invalid argument (R=%d rank=%d B=%d k=%d)", R, rank, B, k);
+        return FRP_E_INVALID;
+    }
+    size_t rec = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
+    rec = (rec + 15) / 16 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_any_status) FRP_CUDA(cudaMemsetAsync(out_any_status, 0, sizeof(int32_t), st));
+    // every block must be resident at once (blocks spin on flags written by other GPUs,
+    // and the flags are only published once all local blocks have pushed)
+    int grid = B < 296 ? B : 296;
+    push_merge_kernel<<<grid, 128, 0, st>>>(metric, R, rank, B, k, (const uint8_t*)send_record,
+                                            (uint8_t* const*)peers_dev, rec, epoch, counter_dev, out_idx,
+                                            out_score, out_count, out_any_status);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
 
 size_t frp_shard_record_bytes(int B, int k) {
     size_t n = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;

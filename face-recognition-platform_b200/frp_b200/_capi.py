@@ -68,6 +68,8 @@ SIGNATURES = {
     "frp_scores_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "frp_shard_record_bytes": (_sz, [_i, _i]),
     "frp_merge_packed_device": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frp_exchange_buffer_bytes": (_sz, [_i, _i, _i]),
+    "frp_push_merge_device": (_i, [_i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "frp_estimate_norm": (_i, [_vp, _i, _vp]),
     "frp_align": (_i, [_i, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp, _vp]),
     "frp_align_device": (_i, [_i, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp, _vp, _vp]),

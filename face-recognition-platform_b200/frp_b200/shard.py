@@ -62,12 +62,20 @@ class ShardedMatcher:
     """
 
     def __init__(self, gallery, total_rows: int, rank: int, world_size: int, group=None,
-                 local_match: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_match: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 exchange: str = "nccl"):
+        """exchange: "nccl" = all_gather_into_tensor + merge kernel; "p2p" = ONE fused kernel
+        that pushes the record into every peer's symmetric-memory buffer over NVLink, waits
+        on system-scope flags and merges (frp_push_merge_device) — no collective call."""
         import torch  # plumbing only: device buffers, streams, the collective
         self.torch = torch
         self.g = gallery
         self.rank, self.world = int(rank), int(world_size)
         self.group = group
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange
+        self._p2p = {}
         self.lo, self.hi = shard_bounds(total_rows, world_size, rank)
         if gallery is not None:
             gallery.set_base(self.lo)
@@ -123,13 +131,52 @@ class ShardedMatcher:
         stream = t.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
         idx, score, count, status = self._views(send, B, k, t)
         self._local_match(q_dev, B, tau, k, flags, idx, score, count, status, stream)
+        m = metric if metric is not None else self.g.metric
+        if self.exchange == "p2p":
+            from ._capi import check, lib, ptr
+            st = self._p2p_state(B, k, device)
+            st["epoch"] += 1
+            check(lib.frp_push_merge_device(int(m), self.world, self.rank, B, k, ptr(send), st["peers_dev"],
+                                            st["epoch"] & 0xFFFFFFFF, ptr(st["counter"]), ptr(out_idx),
+                                            ptr(out_score), ptr(out_count), ptr(any_status), stream or None))
+            return out_idx, out_score, out_count, any_status
         if self.world > 1:
             dist.all_gather_into_tensor(recv, send, group=self.group)
         else:
             recv.copy_(send)
-        m = metric if metric is not None else self.g.metric
         self._merge(m, self.world, B, k, recv, out_idx, out_score, out_count, any_status, stream)
         return out_idx, out_score, out_count, any_status
+
+    def _p2p_state(self, B: int, k: int, device):
+        """Exchange buffer of this rank for (B, k): symmetric memory mapped into every rank
+        (torch.distributed._symmetric_memory = CUDA VMM handles over NVLink), allocated and
+        rendezvoused once; a plain device buffer when there is a single rank."""
+        key = (B, k, str(device))
+        if key in self._p2p:
+            return self._p2p[key]
+        t = self.torch
+        from ._capi import lib
+        nbytes = int(lib.frp_exchange_buffer_bytes(self.world, B, k))
+        if self.world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(nbytes, dtype=t.uint8, device=device)
+            buf.zero_()
+            t.cuda.synchronize(device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            hdl.barrier()                         # every rank's flags are zero before the first push
+            peers_dev = int(hdl.buffer_ptrs_dev)
+            keep = (buf, hdl)
+        else:
+            buf = t.zeros(nbytes, dtype=t.uint8, device=device)
+            ptrs = t.tensor([buf.data_ptr()], dtype=t.int64, device=device)
+            t.cuda.synchronize(device)
+            peers_dev = ptrs.data_ptr()
+            keep = (buf, ptrs)
+        st = {"peers_dev": peers_dev, "counter": t.zeros(1, dtype=t.int32, device=device), "epoch": 0,
+              "keep": keep}
+        self._p2p[key] = st
+        return st
 
     def match_certified(self, q_dev, tau: float, k: int, flags: int = 0, metric: Optional[int] = None):
         """``match`` plus the fallback ladder of the host API: if any shard could not

@@ -138,6 +138,20 @@ int frp_merge_packed_device(int metric, int R, int B, int k, const void* records
                             int64_t* out_idx, float* out_score, int32_t* out_count,
                             int32_t* out_any_status, void* stream);
 
+/* Fused exchange + merge over peer memory (NVLink/NVSwitch), replacing the all-gather:
+ * every rank owns an exchange buffer of frp_exchange_buffer_bytes(R,B,k) bytes that is
+ * mapped into all ranks (CUDA IPC / symmetric memory; zero-initialised once).
+ * peers_dev is a DEVICE array of the R mapped base pointers (index = rank).  One kernel
+ * pushes this rank's packed record into slot [epoch&1][rank] of every peer, publishes a
+ * system-scope flag, waits for the R flags of its own buffer and merges.  `epoch` must
+ * increase by one per call, identically on all ranks; counter_dev is a zero-initialised
+ * device word private to this rank.  Bit 0x100 of *out_any_status = a peer timed out. */
+size_t frp_exchange_buffer_bytes(int R, int B, int k);
+int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void* send_record_dev,
+                          void* const* peers_dev, uint32_t epoch, unsigned int* counter_dev,
+                          int64_t* out_idx, float* out_score, int32_t* out_count,
+                          int32_t* out_any_status, void* stream);
+
 /* ---- alignment: insightface face_align.norm_crop + blobFromImages
  *      (third-party; only call site backend/app/utils/deepfake_utils.py:138) -- */
 /* 2x3 forward similarity matrices from 5 landmarks (skimage _umeyama onto

@@ -89,6 +89,28 @@ def test_match_certified_takes_the_fallback_ladder():
     assert level == 0 and cnt.cpu().numpy().tolist() == [1, 1]
 
 
+def test_fused_push_merge_loopback_equals_allgather_merge():
+    """frp_push_merge_device with one rank (its own exchange buffer as the only peer): the
+    push / flag / wait / merge kernel must give what the all-gather + merge path gives,
+    over several epochs (double-buffered slots)."""
+    G = o.synth_cos_gallery(9000, 512, seed=9)
+    g = Gallery(512, METRIC_COS)
+    g.append(G)
+    a = ShardedMatcher(g, 9000, 0, 1, exchange="p2p")
+    b = ShardedMatcher(g, 9000, 0, 1, exchange="nccl")
+    for step in range(5):
+        Q, _ = o.synth_cos_queries(G, 37, seed=50 + step)
+        q = torch.from_numpy(Q).cuda()
+        ra = [x.clone() for x in a.match(q, 0.3, 10)]
+        rb = [x.clone() for x in b.match(q, 0.3, 10)]
+        torch.cuda.synchronize()
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[2], rb[2])
+        assert torch.equal(torch.nan_to_num(ra[1]), torch.nan_to_num(rb[1]))
+        assert int(ra[3].item()) == 0
+        widx, wsc, wcnt = o.cos_match_topk(G, Q, 0.3, 10, True)
+        assert np.array_equal(ra[0].cpu().numpy(), widx)
+
+
 def test_single_rank_sharded_matcher_runs_end_to_end():
     G = o.synth_cos_gallery(5000, 512, seed=5)
     Q, _ = o.synth_cos_queries(G, 4, seed=6)
