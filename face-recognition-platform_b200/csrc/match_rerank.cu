@@ -385,26 +385,30 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
     const int tid = threadIdx.x;
     const uint32_t par = epoch & 1u;
 
-    // ---- phase 1: push ----
-    {
+    // ---- phase 1: push (a few blocks only; ONE system-scope fence per pushing block: the
+    // block barrier orders the other threads' peer stores before thread 0's fence) ----
+    const unsigned npush = min((unsigned)gridDim.x, (unsigned)(2 * R));
+    if (blockIdx.x < npush) {
         const uint4* src = reinterpret_cast<const uint4*>(send);
         const size_t nvec = rec_bytes / 16;
         const size_t total = nvec * (size_t)R;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)npush * blockDim.x) {
             const int r = (int)(i / nvec);
             const size_t v = i % nvec;
             uint4* dst = reinterpret_cast<uint4*>(peers[r] + kExchHeader + ((size_t)par * R + rank) * rec_bytes);
             dst[v] = src[v];
         }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(block_counter, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence_system();
-        if (tid < R) st_release_sys(reinterpret_cast<uint32_t*>(peers[tid]) + par * 32 + rank, epoch);
-        if (tid == 0) *block_counter = 0u;     // ready for the next launch
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            s_last = (atomicAdd(block_counter, 1u) == npush - 1);
+            if (s_last) {
+                __threadfence_system();
+                for (int r = 0; r < R; ++r)
+                    st_release_sys(reinterpret_cast<uint32_t*>(peers[r]) + par * 32 + rank, epoch);
+                *block_counter = 0u;           // ready for the next launch
+            }
+        }
     }
 
     // ---- phase 2: wait for every rank's record in this rank's buffer ----
