@@ -24,6 +24,35 @@ DEFAULT_CONFIDENCE_THRESHOLD = 0.6   # routes/camera.py:180
 DEFAULT_MAX_FACES = 10               # routes/camera.py:182
 
 
+class CooldownFilter:
+    """Hand-off filter between the matcher and the tracking service:
+    the reference drops a (person, camera) detection that arrives within the cooldown window
+    of the previous recorded one (backend/app/services/tracking_service.py:122-134, window
+    set at :41,57, timestamp stored at :179).  Applying it right after the batched match
+    keeps repeated hits out of the downstream Python services; state is host-side, like the
+    reference's ``last_detection`` dict."""
+
+    def __init__(self, cooldown_seconds: float = 10.0):
+        self.cooldown = float(cooldown_seconds)
+        self.last_detection: Dict[tuple, float] = {}
+
+    def filter(self, results: Dict[Any, List[Dict[str, Any]]], now: float) -> Dict[Any, List[Dict[str, Any]]]:
+        """``results`` = output of ``scan_cameras``; ``now`` = scan timestamp in seconds.
+        Returns the detections the reference's ``record_detection`` would record."""
+        out: Dict[Any, List[Dict[str, Any]]] = {}
+        for cam_id, dets in results.items():
+            kept = []
+            for d in dets:
+                key = (d["target"], cam_id)
+                last = self.last_detection.get(key)
+                if last is not None and (now - last) < self.cooldown:
+                    continue                      # duplicate within the cooldown: not recorded
+                self.last_detection[key] = now
+                kept.append(d)
+            out[cam_id] = kept
+        return out
+
+
 def scan_cameras(service: FaceService, faces_by_camera: Dict[Any, Sequence[np.ndarray]],
                  configs: Optional[Dict[Any, Dict[str, Any]]] = None) -> Dict[Any, List[Dict[str, Any]]]:
     """One scan over all cameras.  ``faces_by_camera[cam_id]`` = the face encodings

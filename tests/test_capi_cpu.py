@@ -141,6 +141,22 @@ def test_gallerydict_rejects_dim_mismatch_and_bulk_load():
         d.bulk_load(["a"], np.zeros((1, 4)))
 
 
+def test_cooldown_filter_matches_reference_semantics():
+    """tracking_service.py:122-134,179: a (person, camera) pair is recorded again only
+    once the cooldown has elapsed since the last RECORDED detection."""
+    from frp_b200.camera_scan import CooldownFilter
+    f = CooldownFilter(10)
+    det = lambda t, c: {"camera_id": c, "target": t, "distance": 0.3, "confidence": "high"}
+    r0 = f.filter({1: [det("a", 1), det("b", 1)], 2: [det("a", 2)]}, now=100.0)
+    assert [d["target"] for d in r0[1]] == ["a", "b"] and len(r0[2]) == 1
+    r1 = f.filter({1: [det("a", 1)], 2: [det("c", 2)]}, now=105.0)
+    assert r1[1] == [] and [d["target"] for d in r1[2]] == ["c"]
+    r2 = f.filter({1: [det("a", 1)]}, now=109.9)          # still measured from t=100, not 105
+    assert r2[1] == []
+    r3 = f.filter({1: [det("a", 1)]}, now=110.0)          # >= cooldown: recorded again
+    assert len(r3[1]) == 1
+
+
 def test_shard_bounds_partition():
     for total in (0, 1, 7, 100, 10_000_019):
         for world in (1, 2, 3, 8):
