@@ -26,7 +26,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("FRP_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -34,7 +34,11 @@ constexpr int kOut = 112;
 constexpr int kTileW = 16;
 constexpr int kTilesX = kOut / kTileW;              // 7
 constexpr int kItemsPerCrop = 2;
-constexpr int kWarps = 10;
+#ifndef FRP_ALIGN_NBUF
+#define FRP_ALIGN_NBUF 1     // measured: 18 single-buffered warps/SM 0.214 ms vs 10 double-buffered 0.227 ms (C4)
+#endif
+constexpr int kNBuf = FRP_ALIGN_NBUF;               // staging buffers per warp (2 = prefetch next tile)
+constexpr int kWarps = (kNBuf == 2) ? 10 : 18;      // what fits in 227 KB of shared memory
 constexpr int kNumW = 5, kNumH = 5;
 __constant__ int c_box_w[kNumW] = {64, 96, 128, 176, 224};   // bytes (multiples of 16)
 __constant__ int c_box_h[kNumH] = {8, 14, 22, 34, 46};       // rows
@@ -43,7 +47,7 @@ constexpr int kHostBoxH[kNumH] = {8, 14, 22, 34, 46};
 constexpr int kMaxBoxW = 224, kMaxBoxH = 46;
 constexpr int kBufBytes = 10368;                    // >= 224*46 + 16 slack, multiple of 128
 constexpr int kTabBytes = 4 * kOut * 4;             // adelta, bdelta, X0, Y0 (1792 = 14*128)
-constexpr int kWarpSmem = 22656;                    // tab + 2 buffers + 2 mbarriers, multiple of 128
+constexpr int kWarpSmem = (kNBuf == 2) ? 22656 : 12288;   // tab + buffers + mbarriers, multiple of 128
 
 struct TmapSet {
     CUtensorMap m[kNumW * kNumH];
@@ -259,6 +263,22 @@ template <int TH>
 __device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& maps, const uint8_t* frame, int fi,
                                           const int* tab, uint32_t buf_saddr0, uint64_t* bars, uint32_t& parity,
                                           int t_begin, int t_end, int lane, __half* oblob, uint8_t* oal) {
+    if (kNBuf == 1) {
+        // single buffer, more resident warps: the TMA latency of one warp is covered by the
+        // blends of the others
+        for (int t = t_begin; t < t_end; ++t) {
+            const TileMeta tm = stage_tile<TH>(a, maps, tab, (t % kTilesX) * kTileW, (t / kTilesX) * TH, fi,
+                                               buf_saddr0, &bars[0], lane);
+            if (!tm.direct) {
+                mbar_wait(&bars[0], parity & 1u);
+                parity ^= 1u;
+            }
+            blend_tile_x<TH>(a, frame, tab, tm, buf_saddr0, (t % kTilesX) * kTileW, (t / kTilesX) * TH, lane,
+                             oblob, oal);
+            __syncwarp();
+        }
+        return;
+    }
     TileMeta cur, nxt;
     cur = stage_tile<TH>(a, maps, tab, (t_begin % kTilesX) * kTileW, (t_begin / kTilesX) * TH, fi, buf_saddr0,
                          &bars[0], lane);
@@ -289,7 +309,7 @@ align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
     uint8_t* wsm = smem + (size_t)warp * kWarpSmem;
     int* tab = reinterpret_cast<int*>(wsm);
     const uint32_t buf_saddr0 = smem_u32(wsm + kTabBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kTabBytes + 2 * kBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kTabBytes + kNBuf * kBufBytes);
     if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
