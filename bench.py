@@ -533,6 +533,37 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     except Exception as e:  # pragma: no cover
         out["align"]["cpu_baseline"] = {"error": str(e)}
 
+    # 128-d L2 (face_recognition encodings) at scale: 4M x 128, tolerance 0.6, batch 1 and 256
+    try:
+        N2_ = 4_000_000
+        g2 = frp.Gallery(128, frp.METRIC_L2, device=device.index or 0, capacity=N2_)
+        gen = torch.Generator(device=device).manual_seed(77)
+        for lo_ in range(0, N2_, 1_000_000):
+            g2.append_device(torch.randn((1_000_000, 128), generator=gen, device=device) * 0.05, stream=st)
+        torch.cuda.synchronize()
+        res = {}
+        for Bx in (1, 256):
+            qx = torch.randn((6, Bx, 128), generator=gen, device=device) * 0.05
+            bo = (torch.empty((Bx, k), dtype=torch.int64, device=device), torch.empty((Bx, k), device=device),
+                  torch.empty((Bx,), dtype=torch.int32, device=device), torch.empty((Bx,), dtype=torch.int32, device=device))
+            _capi.lib.frp_profile_enable(1)
+            ts_ = []
+            for i in range(6):
+                g2.match_device(qx[i], Bx, 0.6, k, 0, *bo, st)
+                pb = C.c_float()
+                _capi.check(_capi.lib.frp_profile_last(None, C.byref(pb), None))
+                if i >= 2:
+                    ts_.append(pb.value / 1e3)
+            _capi.lib.frp_profile_enable(0)
+            tm_ = float(np.mean(ts_))
+            gb_ = N2_ * 256 / 1e9
+            res[str(Bx)] = {"kernel_ms": tm_ * 1e3, "path": frp.last_match_path(), "hbm_gbs": gb_ / tm_,
+                            "hbm_frac": gb_ / tm_ / pk["hbm"], "queries_per_s_kernel": Bx / tm_}
+        out["match_l2_128d"] = {"workload": "L2, tolerance 0.6, 4M x 128 gallery (256 B fp16 rows)", "batches": res}
+        g2.close()
+    except Exception as e:  # pragma: no cover
+        out["match_l2_128d"] = {"error": str(e)}
+
     # config C1: face_recognition compare_faces, 1 query vs 1k synthetic 128-d encodings,
     # tolerance 0.6, through the drop-in FaceService (all 1 000 result dicts, like the reference)
     try:

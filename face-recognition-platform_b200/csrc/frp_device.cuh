@@ -102,11 +102,14 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&k)[E], int lane) {
 // Sums NV (power of two <= 32) per-lane partial values across the warp; on
 // return v[0] of lane l holds the total of value index (l & (NV-1)).
 // Shuffles: NV*log2(32/NV) + NV-1  (instead of 5*NV).
-template <int NV>
+// W (power of two <= 32, >= NV) = width of the lane group that is reduced: groups of W
+// consecutive lanes are summed independently (sub-warp rows for short embeddings).
+template <int NV, int W = 32>
 __device__ __forceinline__ float warp_multi_reduce(float (&v)[NV], int lane) {
+    static_assert(NV <= W && W <= 32, "warp_multi_reduce: NV <= W <= 32");
     // full reductions over the lane bits above log2(NV)
 #pragma unroll
-    for (int s = 16; s >= NV; s >>= 1) {
+    for (int s = W / 2; s >= NV; s >>= 1) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(FRP_FULL_MASK, v[i], s);
     }

@@ -109,7 +109,8 @@ static int alloc_buffers(int dimp, uint64_t cap, __half** g16, float** g32, floa
     cudaError_t e;
     if ((e = cudaMalloc((void**)g16, cap * dimp * sizeof(__half))) != cudaSuccess ||
         (e = cudaMalloc((void**)g32, cap * dimp * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc((void**)norm2, cap * sizeof(float))) != cudaSuccess ||
+        // one tile (256 rows) of slack: the tcgen05 matcher bulk-copies whole 256-row norm tiles
+        (e = cudaMalloc((void**)norm2, (cap + 256) * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void**)alive, cap)) != cudaSuccess) {
         set_error("gallery allocation of %llu rows x %d failed: %s", (unsigned long long)cap, dimp,
                   cudaGetErrorString(e));

@@ -45,6 +45,8 @@ constexpr int kBStageBytes = kTileN * kBlockK * 2;   // 32 KB
 constexpr int kMaxStages = 6;
 constexpr int kAccCols = kTileN;                     // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 512;
+constexpr int kNormSlots = 4;                        // L2 metric: |g|^2 tiles in flight
+constexpr int kNormRingBytes = kNormSlots * kTileN * 4;
 
 struct GemmArgs {
     const uint8_t* alive;
@@ -159,6 +161,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
     uint64_t* afull_bar = bars + 2 * kMaxStages + 4;   // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+    // L2 metric: |g|^2 of the tile's 256 rows travels through its own 4-deep ring (1 KB bulk
+    // copies) so the epilogue reads it from shared memory (broadcast) instead of 256 global
+    // loads per tile per warp
+    uint64_t* nfull_bar = bars + 2 * kMaxStages + 6;    // [kNormSlots]
+    uint64_t* nempty_bar = nfull_bar + kNormSlots;      // [kNormSlots]
+    float* norm_ring = reinterpret_cast<float*>(bars + 32);   // [kNormSlots][kTileN], 256 B after the barriers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qgroup = blockIdx.y;
@@ -173,6 +181,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         mbar_init(afull_bar, 1);
+        for (int s = 0; s < kNormSlots; ++s) { mbar_init(&nfull_bar[s], 1); mbar_init(&nempty_bar[s], 4); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -194,6 +203,16 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         uint32_t ph = 0;
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const int row0 = (int)((blockIdx.x + i * gridDim.x) * kTileN);
+            if (IS_L2) {
+                const uint32_t ns = i % kNormSlots;
+                mbar_wait(&nempty_bar[ns], ((i / kNormSlots) & 1) ^ 1);     // epilogue released the slot
+                if (lane == 0) {
+                    mbar_expect_tx(&nfull_bar[ns], kTileN * 4);
+                    // norm2 is allocated with a tile of slack, so a full tile may always be read
+                    bulk_g2s(norm_ring + ns * kTileN, a.norm2 + row0, kTileN * 4, &nfull_bar[ns]);
+                }
+                __syncwarp();
+            }
             for (int kb = 0; kb < a.nkb; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (lane == 0) {
@@ -260,6 +279,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t as = i & 1;
             const uint32_t row0 = (blockIdx.x + i * gridDim.x) * kTileN;
+            const uint32_t ns = i % kNormSlots;
+            const float* nsm = norm_ring + ns * kTileN;
+            if (IS_L2) mbar_wait(&nfull_bar[ns], (i / kNormSlots) & 1);
             mbar_wait(&tfull_bar[as], (i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols;
@@ -270,11 +292,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 tmem_ld_wait();
                 float sv[32];
                 if (IS_L2) {
-                    // s = 2 g.q - |g|^2 ; the norm is the same address for every lane (broadcast)
+                    // s = 2 g.q - |g|^2 ; every lane reads the same shared-memory words (broadcast)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t row = min(row0 + c + j, a.rows - 1);
-                        sv[j] = fmaf(2.f, __uint_as_float(v[j]), -__ldg(a.norm2 + row));
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 n4 = *reinterpret_cast<const float4*>(nsm + c + j);
+                        sv[j] = fmaf(2.f, __uint_as_float(v[j]), -n4.x);
+                        sv[j + 1] = fmaf(2.f, __uint_as_float(v[j + 1]), -n4.y);
+                        sv[j + 2] = fmaf(2.f, __uint_as_float(v[j + 2]), -n4.z);
+                        sv[j + 3] = fmaf(2.f, __uint_as_float(v[j + 3]), -n4.w);
                     }
                 } else {
 #pragma unroll
@@ -312,7 +337,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                mbar_arrive(&tempty_bar[as]);
+                if (IS_L2) mbar_arrive(&nempty_bar[ns]);
+            }
         }
         if (valid_q) {
             uint64_t* out = a.cand + ((size_t)q * gridDim.x + blockIdx.x) * KP;
@@ -366,8 +394,9 @@ int encode_map(CUtensorMap* map, const void* base, uint64_t rows, int dimp, uint
     return FRP_OK;
 }
 
-int pick_stages(int nkb) {
-    const int budget = 227 * 1024 - 2048 - nkb * kABlockBytes;   // barriers + alignment slack
+int pick_stages(int nkb, bool l2) {
+    // barriers + alignment slack (+ the |g|^2 ring of the L2 epilogue)
+    const int budget = 227 * 1024 - 2048 - nkb * kABlockBytes - (l2 ? kNormRingBytes : 0);
     int st = budget / kBStageBytes;
     if (st > kMaxStages) st = kMaxStages;
     return st;
@@ -403,7 +432,8 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
                       int nlists, cudaStream_t st) {
     const int groups = gemm_groups(B);
     const int nkb = g->dimp / kBlockK;
-    const int stages = pick_stages(nkb);
+    const bool l2 = (g->metric == FRP_METRIC_L2);
+    const int stages = pick_stages(nkb, l2);
     if (stages < 2) { set_error("match_gemm: not enough shared memory for dimp=%d", g->dimp); return FRP_E_UNSUPPORTED; }
     CUtensorMap tq, tg, tgh;
     int rc = encode_map(&tq, q16, (uint64_t)groups * kTileM, g->dimp, kTileM);
@@ -425,7 +455,8 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     a.nkb = nkb;
     a.stages = stages;
     a.metric = g->metric;
-    const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256;
+    const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256 +
+                        (l2 ? kNormRingBytes : 0);
     dim3 grid(nlists, groups);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -451,8 +482,7 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
         }                                                                                                \
         le = cudaLaunchKernelEx(&cfg, match_gemm_kernel<KP_, L2_, CS_>, tq, tg, tgh, a);                 \
     }
-    const bool l2 = (g->metric == FRP_METRIC_L2);
-    const int key = (KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (cs == 2 ? 1 : 0);
+    const int key =(KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (cs == 2 ? 1 : 0);
     if (KP != 16 && KP != 32) { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
     switch (key) {
         case 0: FRP_GEMM_LAUNCH(16, false, 1) break;

@@ -7,13 +7,14 @@
 //
 // Structure (one persistent CTA per SM):
 //   warp 8 (producer): 1-D bulk async copies (TMA engine, cp.async.bulk) of
-//       32 KB gallery chunks into a shared-memory ring, mbarrier-signalled.
-//   warps 0..7 (consumers): each owns RW=4 rows of a chunk; a lane reads its
-//       16-byte slices of the row from shared memory, accumulates QB dot
-//       products in fp32, a transposed warp reduction leaves (row,query) totals
-//       on distinct lanes; score -> cut test -> append to a per-warp candidate
-//       buffer in shared memory, compacted to the running top-KP by a warp
-//       bitonic sort when it fills.  Distances never go to HBM.
+//       16-32 KB gallery chunks into a shared-memory ring, mbarrier-signalled.
+//   warps 0..7 (consumers): a row is spread over LPR = min(32, row bytes / 16) lanes,
+//       so short rows (128-d fp16 = 16 lanes) are processed 32/LPR at a time; a lane
+//       reads its 16-byte slices from shared memory, accumulates QB dot products in
+//       fp32 for RW row slots, a transposed reduction inside each LPR-lane group leaves
+//       the (row, query) totals on distinct lanes; score -> cut test -> append to a
+//       per-warp candidate buffer in shared memory, compacted to the running top-KP by
+//       a warp bitonic sort when it fills.  Distances never go to HBM.
 //   At the end the 8 warps' lists are merged to one top-KP list per query per
 //   CTA: cand[B][nlists][KP] (u64 keys), consumed by the re-rank kernel.
 #pragma once
@@ -26,9 +27,7 @@ namespace frp {
 namespace {
 
 constexpr int kConsumerWarps = 8;
-constexpr int kRW = 4;                             // rows per warp per chunk
-constexpr int kChunkRows = kConsumerWarps * kRW;   // 32 rows per stage
-static_assert(kChunkRows == kScanChunkRows, "chunk size mismatch");
+constexpr int kRW = 4;                             // row slots per warp per chunk (upper bound)
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
@@ -38,6 +37,23 @@ template <int KP> struct CapOf { static constexpr int value = (KP <= 32) ? 64 : 
 template <typename T> struct Vec;
 template <> struct Vec<__half> { static constexpr int n = 8; };
 template <> struct Vec<float> { static constexpr int n = 4; };
+
+// compile-time geometry of one instantiation
+template <typename T, int DIMP, int QB>
+struct Geo {
+    static constexpr int VEC = Vec<T>::n;
+    static constexpr int UNITS = DIMP / VEC;                       // 16-byte units per row
+    static constexpr int LPR = UNITS < 32 ? UNITS : 32;            // lanes per row
+    static constexpr int RPS = 32 / LPR;                           // rows side by side in a warp
+    static constexpr int UPL = UNITS / LPR;                        // units per lane
+    static constexpr int RW = (kRW * QB <= LPR) ? kRW : (LPR / QB);   // keeps NV <= LPR
+    static constexpr int NV = RW * QB;                             // (slot, query) values per lane group
+    static constexpr int WARP_ROWS = RW * RPS;                     // rows per warp per chunk
+    static constexpr int CHUNK_ROWS = kConsumerWarps * WARP_ROWS;  // rows per shared-memory stage
+    static constexpr int ROWBYTES = DIMP * (int)sizeof(T);
+    static constexpr int STAGE_BYTES = CHUNK_ROWS * ROWBYTES;
+    static_assert(RW >= 1 && NV <= LPR && UNITS == LPR * UPL, "unsupported scan geometry");
+};
 
 template <typename T, int VEC>
 __device__ __forceinline__ void unpack16(const uint4& v, float (&f)[VEC]);
@@ -83,13 +99,12 @@ __device__ __forceinline__ int warp_refine(uint64_t* buf, int n, int lane, float
 
 template <typename T, int DIMP, int QB, int KP>
 __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs a) {
-    constexpr int VEC = Vec<T>::n;
-    constexpr int UNITS = DIMP / VEC;                       // 16-byte units per row
-    constexpr int UPL = (UNITS + 31) / 32;                  // units per lane
-    constexpr int ROWBYTES = DIMP * (int)sizeof(T);
-    constexpr int STAGE_BYTES = kChunkRows * ROWBYTES;
+    using G = Geo<T, DIMP, QB>;
+    constexpr int VEC = G::VEC, LPR = G::LPR, RPS = G::RPS, UPL = G::UPL, RW = G::RW, NV = G::NV;
+    constexpr int WARP_ROWS = G::WARP_ROWS, CHUNK_ROWS = G::CHUNK_ROWS;
+    constexpr int ROWBYTES = G::ROWBYTES, STAGE_BYTES = G::STAGE_BYTES;
     constexpr int CAP = CapOf<KP>::value;
-    constexpr int NV = kRW * QB;
+    static_assert(WARP_ROWS <= CAP - KP, "candidate buffer too small for the chunk");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int stages = a.stages;
@@ -121,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
             uint32_t phase = 0;
             for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
                 mbar_wait(&empty_bar[s], phase ^ 1);
-                const uint32_t row0 = c * kChunkRows;
-                const uint32_t nr = min((uint32_t)kChunkRows, a.rows - row0);
+                const uint32_t row0 = c * CHUNK_ROWS;
+                const uint32_t nr = min((uint32_t)CHUNK_ROWS, a.rows - row0);
                 const uint32_t bytes = nr * ROWBYTES;
                 mbar_expect_tx(&full_bar[s], bytes);
                 bulk_g2s(ring + (size_t)s * STAGE_BYTES,
@@ -135,22 +150,25 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
     }
 
     // ===== consumers =====
-    // query slices in registers: element e of unit (lane + 32 j) is q[(lane+32j)*VEC + t]
+    const int sub = lane / LPR;          // which of the RPS side-by-side rows
+    const int lu = lane % LPR;           // unit index inside the row (first of UPL)
+    // query slices in registers: element t of unit (lu + LPR j) is q[(lu + LPR j)*VEC + t]
     float qreg[QB][UPL * VEC];
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) {
         const int qg = min(qbase + qi, a.B - 1);
 #pragma unroll
         for (int j = 0; j < UPL; ++j) {
-            const int u = lane + 32 * j;
+            const int u = lu + LPR * j;
 #pragma unroll
-            for (int t = 0; t < VEC; ++t)
-                qreg[qi][j * VEC + t] = (u < UNITS) ? a.q[(size_t)qg * DIMP + u * VEC + t] : 0.f;
+            for (int t = 0; t < VEC; ++t) qreg[qi][j * VEC + t] = a.q[(size_t)qg * DIMP + u * VEC + t];
         }
     }
-    // lane l < NV finishes value index l = r*QB + qi
-    const int my_r = (lane & (NV - 1)) / QB;
-    const int my_qi = (lane & (NV - 1)) % QB;
+    // inside its lane group, lane lu < NV finishes value index lu = slot*QB + qi
+    const bool res_lane = lu < NV;
+    const int my_slot = (lu & (NV - 1)) / QB;
+    const int my_qi = (lu & (NV - 1)) % QB;
+    const int my_row_in_warp = my_slot * RPS + sub;
     const bool my_valid_q = (qbase + my_qi) < a.B;
     float my_cut = my_valid_q ? a.qp[qbase + my_qi].cut0 : __int_as_float(0x7f800000);
     uint64_t* my_buf = wbuf + ((size_t)warp * QB + my_qi) * CAP;
@@ -160,33 +178,31 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
     int s = 0;
     uint32_t phase = 0;
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const uint32_t row_l = c * kChunkRows + warp * kRW + my_r;   // this lane's result row
+        const uint32_t row_l = c * CHUNK_ROWS + warp * WARP_ROWS + my_row_in_warp;   // this lane's result row
         float n2 = 0.f;
-        if (is_l2 && lane < NV && row_l < a.rows) n2 = __ldg(a.norm2 + row_l);
+        if (is_l2 && res_lane && row_l < a.rows) n2 = __ldg(a.norm2 + row_l);
 
         mbar_wait(&full_bar[s], phase);
-        const uint8_t* base = ring + (size_t)s * STAGE_BYTES + (size_t)(warp * kRW) * ROWBYTES;
+        const uint8_t* base = ring + (size_t)s * STAGE_BYTES + (size_t)(warp * WARP_ROWS + sub) * ROWBYTES;
         float acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < UPL; ++j) {
-            const int u = lane + 32 * j;
-            if (UNITS >= 32 * (j + 1) || u < UNITS) {
-                uint4 v[kRW];
+            const int u = lu + LPR * j;
+            uint4 v[RW];
 #pragma unroll
-                for (int r = 0; r < kRW; ++r)
-                    v[r] = *reinterpret_cast<const uint4*>(base + r * ROWBYTES + u * 16);
+            for (int r = 0; r < RW; ++r)
+                v[r] = *reinterpret_cast<const uint4*>(base + (size_t)(r * RPS) * ROWBYTES + u * 16);
 #pragma unroll
-                for (int r = 0; r < kRW; ++r) {
-                    float f[VEC];
-                    unpack16<T, VEC>(v[r], f);
+            for (int r = 0; r < RW; ++r) {
+                float f[VEC];
+                unpack16<T, VEC>(v[r], f);
 #pragma unroll
-                    for (int qi = 0; qi < QB; ++qi) {
+                for (int qi = 0; qi < QB; ++qi) {
 #pragma unroll
-                        for (int t = 0; t < VEC; ++t)
-                            acc[r * QB + qi] = fmaf(f[t], qreg[qi][j * VEC + t], acc[r * QB + qi]);
-                    }
+                    for (int t = 0; t < VEC; ++t)
+                        acc[r * QB + qi] = fmaf(f[t], qreg[qi][j * VEC + t], acc[r * QB + qi]);
                 }
             }
         }
@@ -194,9 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
         if (lane == 0) mbar_arrive(&empty_bar[s]);   // stage consumed (data is in registers)
         if (++s == stages) { s = 0; phase ^= 1; }
 
-        float sc = warp_multi_reduce<NV>(acc, lane);
+        float sc = warp_multi_reduce<NV, LPR>(acc, lane);
         if (is_l2) sc = 2.f * sc - n2;
-        const bool pass = (lane < NV) && (row_l < a.rows) && (sc >= my_cut);
+        const bool pass = res_lane && (row_l < a.rows) && (sc >= my_cut);
         const unsigned m = __ballot_sync(FRP_FULL_MASK, pass);
         if (m) {
             if (pass && a.alive[row_l]) {
@@ -208,17 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
             for (int qi = 0; qi < QB; ++qi) {
                 int* cnt = wcnt + warp * QB + qi;
                 const int n = *cnt;
-                if (n > CAP - kRW) {   // warp-uniform
-                    float cut = 0.f;
-                    bool upd = false;
+                if (n > CAP - WARP_ROWS) {   // warp-uniform: the next chunk could overflow the buffer
                     float nc = 0.f;
                     __syncwarp();
-                    const int kept = warp_refine<KP, CAP>(wbuf + ((size_t)warp * QB + qi) * CAP, n,
-                                                          lane, &nc);
-                    upd = (n >= KP);
-                    cut = nc;
+                    const int kept = warp_refine<KP, CAP>(wbuf + ((size_t)warp * QB + qi) * CAP, n, lane, &nc);
                     if (lane == 0) *cnt = kept;
-                    if (upd && my_qi == qi && cut > my_cut) my_cut = cut;
+                    if (n >= KP && my_qi == qi && nc > my_cut) my_cut = nc;
                     __syncwarp();
                 }
             }
@@ -256,13 +267,11 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
     }
 }
 
-template <typename T, int DIMP>
-constexpr int stage_bytes() { return kChunkRows * DIMP * (int)sizeof(T); }
-
 template <typename T, int DIMP, int QB, int KP>
 int launch_one(const ScanArgs& a, int nlists, int qgroups, cudaStream_t st) {
+    using G = Geo<T, DIMP, QB>;
     constexpr int CAP = CapOf<KP>::value;
-    constexpr int SB = stage_bytes<T, DIMP>();
+    constexpr int SB = G::STAGE_BYTES;
     int stages = kSmemBudget / SB;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
@@ -277,6 +286,9 @@ int launch_one(const ScanArgs& a, int nlists, int qgroups, cudaStream_t st) {
     }
     ScanArgs b = a;
     b.stages = stages;
+    // chunk size depends on the instantiation; CTAs beyond the last chunk just emit empty lists
+    // (gridDim.x must stay `nlists`: it is the candidate stride the re-rank kernel reads)
+    b.nchunks = (uint32_t)((a.rows + G::CHUNK_ROWS - 1) / G::CHUNK_ROWS);
     dim3 grid(nlists, qgroups);
     kern<<<grid, kThreads, smem, st>>>(b);
     FRP_CHECK_LAUNCH();
