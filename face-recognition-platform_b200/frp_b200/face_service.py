@@ -115,24 +115,26 @@ class FaceService:
             v = all_v[rows]
             matches = self._is_match(v, self.tolerance)
             key = self._value_key()
-            results: List[Dict[str, Any]] = []
             now = datetime.now().isoformat()
-            for i, target in enumerate(names):
-                val = float(v[i])
-                item: Dict[str, Any] = {"target": target, "match": bool(matches[i])}
-                if return_distances:
-                    item[key] = val
-                    if not self._cos:
-                        item["confidence"] = self._get_confidence_level(val)
-                        item["confidence_score"] = self._calibrate_confidence(val)
-                results.append(item)
-                self._comparison_history.append({key: val, "match": bool(matches[i]), "timestamp": now})
-            if return_distances:
-                # stable: ties keep dict insertion order (face_service.py:431)
+            vals, ms = v.tolist(), matches.tolist()
+            self._comparison_history.extend({key: vals[i], "match": ms[i], "timestamp": now}
+                                            for i in range(len(names)))
+            if not return_distances:
+                results = [{"target": names[i], "match": ms[i]} for i in range(len(names))]
+            else:
+                # stable argsort == the reference's stable list.sort: ties keep dict
+                # insertion order (face_service.py:431)
+                order = np.argsort(-v if self._cos else v, kind="stable").tolist()
                 if self._cos:
-                    results.sort(key=lambda x: -x.get(key, -1.0))
+                    results = [{"target": names[i], "match": ms[i], key: vals[i]} for i in order]
                 else:
-                    results.sort(key=lambda x: x.get(key, 1.0))
+                    # vectorised _get_confidence_level / _calibrate_confidence (same formulas)
+                    lv = np.where(v < 0.4, 0, np.where(v < 0.6, 1, 2)).tolist()
+                    x = np.clip(1.0 - v, 0.0, 1.0)
+                    cal = (100.0 / (1.0 + np.exp(-12.0 * (x - 0.5)))).tolist()
+                    lvn = ("high", "medium", "low")
+                    results = [{"target": names[i], "match": ms[i], key: vals[i], "confidence": lvn[lv[i]],
+                                "confidence_score": round(cal[i], 2)} for i in order]
             dt = time.time() - start_time
             with self._metrics_lock:
                 self._metrics["total_comparisons"] += len(names)
