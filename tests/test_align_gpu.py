@@ -80,9 +80,11 @@ def test_fully_outside_and_degenerate():
 
 
 def test_device_path_many_crops():
+    """BASELINE.json configs[3] at full size: 4 096 detections from 16 1080p frames."""
     import torch
-    F, H, W, per = 4, 1080, 1920, 256
-    frames = o.synth_frames(F, H, W, seed=51)
+    F, H, W, per = 16, 1080, 1920, 256
+    frames = np.random.default_rng(51).integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    frames[:2] = o.synth_frames(2, H, W, seed=51)       # two smooth frames, the rest white noise
     fi, lm = o.synth_detections(F, per, seed=52)
     n = len(fi)
     d_fr = torch.from_numpy(frames).cuda()

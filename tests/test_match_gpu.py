@@ -446,6 +446,61 @@ def test_concurrent_callers():
 
 
 # ----------------------------------------------------------------------------
+# BASELINE.json's full size (10M x 512, batch 256, top-10): size-independent properties
+# ----------------------------------------------------------------------------
+def test_full_size_10m_properties():
+    import torch
+    N, D, B, k, tau = 10_000_000, 512, 256, 10, 0.40
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    full = Gallery(D, METRIC_COS, capacity=N)
+    halves = [Gallery(D, METRIC_COS, capacity=N // 2) for _ in range(2)]
+    halves[1].set_base(N // 2)
+    chunk = 1_000_000
+    keep = []
+    for lo in range(0, N, chunk):
+        x = torch.randn((chunk, D), generator=gen, device="cuda", dtype=torch.float32)
+        full.append_device(x)
+        halves[lo // (N // 2)].append_device(x)
+        keep.append(x[:16].cpu().numpy())
+        del x
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(12)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    planted = {}
+    for j in range(0, B, 2):                       # every other query is planted
+        c = int(rng.integers(0, N // chunk))
+        r = int(rng.integers(0, 16))
+        base = keep[c][r] / np.linalg.norm(keep[c][r])
+        a = rng.uniform(0.6, 0.95)
+        Q[j] = a * base + np.sqrt(1 - a * a) * Q[j] / np.linalg.norm(Q[j])
+        want = float(Q[j].astype(np.float64) @ base.astype(np.float64) / np.linalg.norm(Q[j].astype(np.float64)))
+        planted[j] = (c * chunk + r, want)
+    idx, sc, cnt, st = full.match(Q, tau, k)
+    assert frp_b200.last_match_path() == "gemm_tcgen05" and np.all(st == 0)
+    for j in range(B):
+        if j in planted:                           # planted recall, score ~ alpha
+            assert idx[j, 0] == planted[j][0] and abs(sc[j, 0] - planted[j][1]) < 1e-5, j
+        else:                                      # impostors stay below 0.40 at 10M rows
+            assert cnt[j] == 0
+    # pure top-k: prefix / monotone / batch-1 scan path agrees with the tensor-core path
+    i2, s2, c2, st2 = full.match(Q, tau, k, MATCH_NO_THRESHOLD)
+    assert np.all(st2 == 0) and np.all(c2 == k) and np.all(np.diff(s2, axis=1) <= 0)
+    for j in range(B):
+        assert np.array_equal(i2[j, :cnt[j]], idx[j, :cnt[j]])
+    for j in (0, 1, 101, 254):
+        i1, s1, c1, _ = full.match(Q[j:j + 1], tau, k, MATCH_NO_THRESHOLD)
+        assert frp_b200.last_match_path() == "scan_f16"
+        assert np.array_equal(i1[0], i2[j]) and np.array_equal(s1[0], s2[j])
+    # shard invariance at full size: two 5M shards merged == one 10M gallery
+    parts = [h.match(Q, tau, k, MATCH_NO_THRESHOLD) for h in halves]
+    for j in range(B):
+        ent = [(-float(p[1][j, t]), int(p[0][j, t])) for p in parts for t in range(int(p[2][j]))]
+        ent.sort()
+        assert [e[1] for e in ent[:k]] == i2[j].tolist()
+        assert np.array_equal(np.array([-e[0] for e in ent[:k]], np.float32), s2[j])
+
+
+# ----------------------------------------------------------------------------
 # size-independent properties at a large size (1M x 512; oracle too slow here)
 # ----------------------------------------------------------------------------
 def test_properties_large():
