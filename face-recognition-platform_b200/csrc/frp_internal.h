@@ -26,8 +26,9 @@ struct frp_gallery {
     float* g32 = nullptr;    // [capacity][dimp] fp32 master (COS: normalised)
     float* norm2 = nullptr;  // [capacity] |g|^2 of the master row
     uint8_t* alive = nullptr;  // [capacity] 1 = live, 0 = tombstone
-    float* d_gmax = nullptr;   // device scalar: max |g| seen (monotone upper bound)
-    float gmax = 0.f;          // host copy
+    float* d_gmax = nullptr;   // device [2]: max |g| seen, max |g - fp16(g)| seen (monotone upper bounds)
+    float gmax = 0.f;          // host copies
+    float gerr = 0.f;
     int sm_count = FRP_NUM_SM_DEFAULT;
     void* tmap_g16 = nullptr;     // CUtensorMap for the tcgen05 matcher (lazily encoded)
     uint64_t tmap_rows = 0;       // rows the tensor map was encoded for
@@ -88,15 +89,15 @@ __host__ __device__ inline uint64_t make_key(float s, uint32_t row) {
 __host__ __device__ inline float key_score(uint64_t k) { return f32_from_orderable((uint32_t)(k >> 32)); }
 __host__ __device__ inline uint32_t key_row(uint64_t k) { return ~(uint32_t)(k & 0xffffffffu); }
 
-// error-bound coefficients (relative to |g||q|), see DESIGN.md "exactness certificate"
-inline float eps_coeff_scan_f16(int dimp) { return 1.02f * 4.8828125e-4f + (float)dimp * 6.0e-8f + 1e-6f; }
-inline float eps_coeff_gemm_f16(int dimp) { return 1.02f * 9.765625e-4f + (float)dimp * 1.2e-7f + 1e-6f; }
-inline float eps_coeff_scan_f32(int dimp) { return (float)dimp * 1.2e-7f + 1e-7f; }
+// prefilter error-bound modes (see DESIGN.md "exactness certificate")
+#define FRP_EPS_SCAN_F16 0   /* fp16 gallery copy x fp32 query */
+#define FRP_EPS_GEMM_F16 1   /* fp16 gallery copy x fp16 query (tcgen05) */
+#define FRP_EPS_SCAN_F32 2   /* fp32 master x fp32 query */
 
 // ---- kernels / launchers (defined in the .cu files) --------------------------
 // prep: normalise (COS), pad to dimp, make fp16 copy, fill QParams
 int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
-                        float eps_coeff, float* qprep, __half* q16, QParams* qp, cudaStream_t st);
+                        int eps_mode, float* qprep, __half* q16, QParams* qp, cudaStream_t st);
 
 // streaming scan prefilter: writes cand[B][nlists][KP] keys. use_master: scan fp32 master.
 int scan_num_lists(const frp_gallery* g, bool use_master);

@@ -52,21 +52,30 @@ __global__ void ingest_rows_kernel(const float* __restrict__ src, uint64_t n, in
     double scale = 1.0;
     if (metric == FRP_METRIC_COS) scale = acc > 0.0 ? 1.0 / sqrt(acc) : 0.0;
     const uint64_t row = first_row + w;
-    double acc2 = 0.0;
+    double acc2 = 0.0, err2 = 0.0;
     for (int i = lane; i < dimp; i += 32) {
         float v = 0.f;
         if (i < dim) v = (float)((double)s[i] * scale);
+        const __half h = __float2half_rn(v);
         g32[row * dimp + i] = v;
-        g16[row * dimp + i] = __float2half_rn(v);
+        g16[row * dimp + i] = h;
         acc2 += (double)v * (double)v;
+        const double d = (double)v - (double)__half2float(h);      // inf - x = inf on fp16 overflow
+        err2 += d * d;
     }
     acc2 = warp_sum_f64(acc2);
+    err2 = warp_sum_f64(err2);
     if (lane == 0) {
         norm2[row] = (float)acc2;
         alive[row] = 1;
-        // monotone upper bound of |g| (rounded up); positive floats order like ints
+        // gmax[0]: monotone upper bound of |g|; gmax[1]: of |g - fp16(g)|, the ACTUAL rounding
+        // error of the scan copy (rigorous prefilter bound by Cauchy-Schwarz, any scale).
+        // Rounded up; non-negative floats order like ints.
         const float nr = __double2float_ru(sqrt(acc2));
+        float er = __double2float_ru(sqrt(err2));
+        if (!(er == er)) er = __int_as_float(0x7f800000);
         atomicMax((int*)gmax, __float_as_int(nr));
+        atomicMax((int*)gmax + 1, __float_as_int(er));
     }
 }
 
@@ -158,8 +167,11 @@ static int ingest_device(frp_gallery* g, const float* src, uint64_t n, uint64_t 
 }
 
 static int refresh_gmax(frp_gallery* g, cudaStream_t st) {
-    FRP_CUDA(cudaMemcpyAsync(&g->gmax, g->d_gmax, sizeof(float), cudaMemcpyDeviceToHost, st));
+    float both[2] = {0.f, 0.f};
+    FRP_CUDA(cudaMemcpyAsync(both, g->d_gmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     FRP_CUDA(cudaStreamSynchronize(st));
+    g->gmax = both[0];
+    g->gerr = both[1];
     return FRP_OK;
 }
 
@@ -256,8 +268,8 @@ int frp_gallery_create(int device, int dim, int metric, uint64_t capacity, frp_g
     rc = alloc_buffers(g->dimp, capacity, &g->g16, &g->g32, &g->norm2, &g->alive);
     if (rc) { delete g; return rc; }
     g->capacity = capacity;
-    cudaError_t e = cudaMalloc((void**)&g->d_gmax, sizeof(float));
-    if (e == cudaSuccess) e = cudaMemset(g->d_gmax, 0, sizeof(float));
+    cudaError_t e = cudaMalloc((void**)&g->d_gmax, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(g->d_gmax, 0, 2 * sizeof(float));
     if (e != cudaSuccess) {
         set_error("gallery scalar allocation failed: %s", cudaGetErrorString(e));
         free_buffers(g);
@@ -414,7 +426,9 @@ int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, 
     }
     ng->rows = n;
     ng->gmax = g->gmax;
-    cudaMemcpy(ng->d_gmax, &ng->gmax, sizeof(float), cudaMemcpyHostToDevice);
+    ng->gerr = g->gerr;
+    const float both[2] = {ng->gmax, ng->gerr};
+    cudaMemcpy(ng->d_gmax, both, 2 * sizeof(float), cudaMemcpyHostToDevice);
     *out = ng;
     return FRP_OK;
 }

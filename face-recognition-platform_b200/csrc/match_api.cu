@@ -70,8 +70,7 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
         return FRP_E_UNSUPPORTED;
     }
     const int nlists = use_gemm ? gemm_num_lists(g, B) : scan_num_lists(g, exact);
-    const float ec = exact ? eps_coeff_scan_f32(g->dimp)
-                           : (use_gemm ? eps_coeff_gemm_f16(g->dimp) : eps_coeff_scan_f16(g->dimp));
+    const int ec = exact ? FRP_EPS_SCAN_F32 : (use_gemm ? FRP_EPS_GEMM_F16 : FRP_EPS_SCAN_F16);
 
     const size_t qprep_bytes = (size_t)B * g->dimp * sizeof(float);
     const size_t q16_bytes = (size_t)(((B + 127) / 128) * 128) * g->dimp * sizeof(__half);
@@ -281,7 +280,8 @@ int frp_scores_device(frp_gallery_t* g, const float* queries_dev, int B, double*
     FRP_CUDA(cudaMallocAsync((void**)&ws, qprep_bytes + (size_t)B * sizeof(QParams) + 256, st));
     float* qprep = reinterpret_cast<float*>(ws);
     QParams* qp = reinterpret_cast<QParams*>(ws + ((qprep_bytes + 255) & ~(size_t)255));
-    int rc = launch_prep_queries(g, queries_dev, B, 0.0, FRP_MATCH_NO_THRESHOLD, 0.f, qprep, nullptr, qp, st);
+    int rc = launch_prep_queries(g, queries_dev, B, 0.0, FRP_MATCH_NO_THRESHOLD, FRP_EPS_SCAN_F32, qprep, nullptr,
+                                 qp, st);
     if (!rc) rc = launch_scores(g, qprep, B, out_dev, st);
     cudaFreeAsync(ws, st);
     return rc;

@@ -24,11 +24,15 @@ __device__ __forceinline__ float float_round_down(double x) {
 // ---------------------------------------------------------------------------
 // prep_queries: one block per query.
 // ---------------------------------------------------------------------------
+// eps_mode: 0 = fp16 gallery x fp32 query (scan), 1 = fp16 x fp16 (tcgen05), 2 = fp32 master
+// scan.  The prefilter error bound is rigorous at any scale (Cauchy-Schwarz on the MEASURED
+// rounding errors): |s~ - s| <= |g16-g|*|q16| + |g|*|q16-q| + fp32 accumulation.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int dim, int dimp, int metric,
-                                    double tau, int flags, float eps_coeff, float gmax,
+                                    double tau, int flags, int eps_mode, float gmax, float gerr,
                                     float* __restrict__ qprep, __half* __restrict__ q16,
                                     QParams* __restrict__ qp) {
     __shared__ double red[32];
+    __shared__ double red2[32];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float* src = q + (size_t)b * dim;
@@ -50,21 +54,42 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int dim, int di
     const double nrm = sqrt(n2);
     double scale = 1.0;
     if (metric == FRP_METRIC_COS) scale = n2 > 0.0 ? 1.0 / nrm : 0.0;
+    double qe2 = 0.0, qp2 = 0.0;      // |q16 - q|^2 and |q|^2 of the prepared query
     for (int i = tid; i < dimp; i += blockDim.x) {
         const float v = (i < dim) ? (float)((double)src[i] * scale) : 0.f;
         qprep[(size_t)b * dimp + i] = v;
-        if (q16) q16[(size_t)b * dimp + i] = __float2half_rn(v);
+        qp2 += (double)v * (double)v;
+        if (q16) {
+            const __half h = __float2half_rn(v);
+            q16[(size_t)b * dimp + i] = h;
+            const double d = (double)v - (double)__half2float(h);
+            qe2 += d * d;
+        }
     }
+    qe2 = warp_sum_f64(qe2);
+    qp2 = warp_sum_f64(qp2);
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = qe2; red2[tid >> 5] = qp2; }
+    __syncthreads();
     if (tid == 0) {
+        double e2 = 0.0, p2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { e2 += red[w]; p2 += red2[w]; }
         QParams p;
         const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        const float qn = __double2float_ru(sqrt(p2)) * 1.000001f;               // |q| (prepared)
+        float qerr = (eps_mode == 1) ? __double2float_ru(sqrt(e2)) : 0.f;     // |q16 - q|
+        if (!(qerr == qerr)) qerr = __int_as_float(0x7f800000);
+        const float ge = (eps_mode == 2) ? 0.f : gerr;
+        // operand rounding (exact bound) + fp32 accumulation (2^-23 per term, truncating adders)
+        const float eps_dot = ge * (qn + qerr) + gmax * qerr +
+                              (float)dimp * 1.2e-7f * (gmax + ge) * (qn + qerr);
         if (metric == FRP_METRIC_COS) {
-            p.eps = eps_coeff * fmaxf(gmax, 1.f) * 1.000001f;
+            p.eps = eps_dot * 1.0001f + 1e-7f;
             p.s_thresh = tau;
             p.qnorm2 = 1.0;
         } else {
-            const float qn = __double2float_ru(nrm);
-            p.eps = 2.f * eps_coeff * gmax * qn + 2.4e-7f * (gmax * gmax + 2.f * gmax * qn) + 1e-12f;
+            // s = 2 g.q - |g|^2: twice the dot error + rounding of the stored norm and of the fma
+            p.eps = 2.f * eps_dot * 1.0001f + 2.4e-7f * (gmax * gmax + 2.f * gmax * qn) + 1e-12f;
             p.s_thresh = (tau >= 0.0) ? (n2 - tau * tau) : inf;
             p.qnorm2 = n2;
         }
@@ -240,7 +265,9 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs
     //    (or < cut0), hence s_exact <= Lfull + eps (or < s_thresh).
     if (tid == 0) {
         a.out_count[b] = cnt;
-        bool ok = !overflow;
+        // a non-finite bound (fp16 overflow of the gallery copy or of the query) certifies nothing:
+        // NaN/inf approximate scores never enter the lists
+        bool ok = !overflow && (qp.eps < 3.0e38f);
         const bool lf_valid = s_lfull != 0u;
         const double bound = (double)f32_from_orderable(s_lfull) + (double)qp.eps;
         if (lf_valid) {
@@ -478,9 +505,9 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
 }  // namespace
 
 int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
-                        float eps_coeff, float* qprep, __half* q16, QParams* qp, cudaStream_t st) {
-    prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, g->dim, g->dimp, g->metric, tau, flags, eps_coeff,
-                                           g->gmax, qprep, q16, qp);
+                        int eps_mode, float* qprep, __half* q16, QParams* qp, cudaStream_t st) {
+    prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, g->dim, g->dimp, g->metric, tau, flags, eps_mode,
+                                           g->gmax, g->gerr, qprep, q16, qp);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }

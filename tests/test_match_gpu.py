@@ -355,6 +355,35 @@ def test_exact_ties_and_inclusive_threshold(seed):
             assert np.all(st <= 1)
 
 
+@pytest.mark.parametrize("scale", [1e-6, 3e-3, 40.0, 2e5])
+def test_extreme_scales_stay_exact(scale):
+    """The prefilter bound is computed from the MEASURED fp16 rounding error of the gallery
+    and the query (Cauchy-Schwarz), so it stays rigorous for subnormal-range and
+    overflowing (fp16 inf) encodings; those queries are answered by the fp32 fallback."""
+    rng = np.random.default_rng(int(scale * 1e7) % 1000)
+    N, dim, B, k = 3000, 128, 6, 5
+    G = (rng.normal(0, 1.0, (N, dim)) * scale).astype(np.float32)
+    Q = (G[rng.integers(0, N, B)] + rng.normal(0, 0.3, (B, dim)) * scale).astype(np.float32)
+    D = np.stack([np.linalg.norm(G.astype(np.float64) - q.astype(np.float64), axis=1) for q in Q])
+    tau = float(np.sort(D[0])[12])
+    widx, wd, wcnt = o.l2_match_topk(G, Q, tau, k, True)
+    gal = Gallery(dim, METRIC_L2)
+    gal.append(G)
+    for path in (MATCH_FORCE_SCAN, MATCH_FORCE_GEMM, 0):
+        idx, sc, cnt, st = gal.match(Q, tau, k, path)
+        assert np.array_equal(cnt, wcnt.astype(np.int32)) and np.array_equal(idx, widx), (scale, path)
+        for b in range(B):
+            assert np.allclose(sc[b, :cnt[b]], wd[b, :cnt[b]], rtol=2e-6, atol=0)
+        assert np.all(st <= 1)
+    # cosine is scale-free after normalisation
+    gc = Gallery(dim, METRIC_COS)
+    gc.append(G)
+    S = o.cosine_scores(G, Q)
+    widx, wsc, wcnt = o.cos_match_topk(G, Q, 0.5, k, True)
+    idx, sc, cnt, st = gc.match(Q, 0.5, k)
+    assert np.array_equal(idx, widx) and np.array_equal(cnt, wcnt.astype(np.int32)) and np.all(st == 0)
+
+
 # ----------------------------------------------------------------------------
 # edge cases
 # ----------------------------------------------------------------------------
