@@ -456,6 +456,30 @@ def test_snapshot_roundtrip(tmp_path):
     assert a[2].sum() >= 2
 
 
+def test_documents_and_named_snapshot(tmp_path):
+    """Row N3: start-up load from db.py-style documents (Fernet), then a named snapshot."""
+    from cryptography.fernet import Fernet
+    from frp_b200.persistence import encode_embedding, load_faces, load_snapshot, save_snapshot
+    G = o.synth_l2_gallery(400, 128, seed=31)
+    key = Fernet.generate_key()
+    docs = [{"target": "p%03d" % i, "embedding": encode_embedding(g.tolist(), key)} for i, g in enumerate(G)]
+    enc = GalleryDict()
+    assert load_faces(enc, docs, key) == 400
+    fs = FaceService(enc, raise_errors=True)
+    ref = {"p%03d" % i: g.tolist() for i, g in enumerate(G)}
+    q = G[7] + 0.002
+    want = o.compare_faces(ref, q, 0.6)
+    got = fs.compare_faces(q)
+    assert [r["target"] for r in got] == [r["target"] for r in want] and got[0]["target"] == "p007"
+    del enc["p003"]
+    p = str(tmp_path / "gallery.frp")
+    save_snapshot(enc, p)
+    enc2 = load_snapshot(p)
+    assert enc2.keys() == enc.keys() and "p003" not in enc2
+    got2 = FaceService(enc2, raise_errors=True).compare_faces(q)
+    assert [(r["target"], r["distance"]) for r in got2] == [(r["target"], r["distance"]) for r in fs.compare_faces(q)]
+
+
 def test_concurrent_callers():
     # routes/camera.py:30 calls compare_faces from a 4-thread pool
     from concurrent.futures import ThreadPoolExecutor
