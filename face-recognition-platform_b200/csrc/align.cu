@@ -10,8 +10,9 @@
 // (TH = 16, or 8 for large faces); per tile ONE 3-D tiled TMA load
 // (cp.async.bulk.tensor, SASS UTMALDG) stages the source bounding box of the tile —
 // bytes x rows x frame, zero-filled outside the frame, which IS BORDER_CONSTANT 0 —
-// into the warp's private shared-memory buffer, double buffered against the blend of
-// the previous tile through two mbarriers.  Box sizes come from a 5x5 ladder of tensor
+// into the warp's private shared-memory buffer and completes on the warp's mbarrier; 18
+// warps per SM hide each other's TMA latency (FRP_ALIGN_NBUF=2 builds the double-buffered
+// 10-warp variant, measured slower).  Box sizes come from a 5x5 ladder of tensor
 // maps so small faces do not over-fetch (the inner TMA coordinate must be 16-byte
 // aligned, so boxes start at floor16(3*sx_min)).  Lanes are mapped x-major (16 columns x
 // 2 rows per warp instruction): each lane produces TH/2 output pixels from shared memory

@@ -30,9 +30,6 @@ struct frp_gallery {
     float gmax = 0.f;          // host copies
     float gerr = 0.f;
     int sm_count = FRP_NUM_SM_DEFAULT;
-    void* tmap_g16 = nullptr;     // CUtensorMap for the tcgen05 matcher (lazily encoded)
-    uint64_t tmap_rows = 0;       // rows the tensor map was encoded for
-    const void* tmap_ptr = nullptr;
     mutable std::shared_mutex mu;  // match = shared, mutate = unique
 };
 

@@ -287,7 +287,6 @@ int frp_gallery_destroy(frp_gallery_t* g) {
         cudaDeviceSynchronize();
         free_buffers(g);
         if (g->d_gmax) cudaFree(g->d_gmax);
-        if (g->tmap_g16) free(g->tmap_g16);
     }
     delete g;
     return FRP_OK;

@@ -21,7 +21,15 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 of their TMEM lane quadrant, cut test,
 //            register top-KP insert; double-buffered against the MMA through two
 //            256-column accumulator stages.
+// Batches of 129..256 (any even number of 128-query groups) run as clusters of two CTAs
+// that stream the SAME gallery tiles: each CTA fetches half of every tile and
+// TMA-multicasts it into both CTAs' shared memory (UTMALDG.2D.MULTICAST), the smem slot
+// is released in both by a multicast tcgen05.commit — half the L2 -> SM traffic.
+// L2 metric: |g|^2 of each tile reaches the epilogue through a 4-slot bulk-copy ring.
 // Output contract is the scan kernel's: cand[B][nlists][KP] u64 keys.
+//
+// Not taken this round: the cta_group::2 (M=256 pair MMA) form of the same kernel; a first
+// attempt faulted in its barrier/TMA plumbing and was reverted ("next").
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
