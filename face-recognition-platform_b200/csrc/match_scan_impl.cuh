@@ -27,7 +27,6 @@ namespace frp {
 namespace {
 
 constexpr int kConsumerWarps = 8;
-constexpr int kRW = 4;                             // row slots per warp per chunk (upper bound)
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
@@ -46,11 +45,14 @@ struct Geo {
     static constexpr int LPR = UNITS < 32 ? UNITS : 32;            // lanes per row
     static constexpr int RPS = 32 / LPR;                           // rows side by side in a warp
     static constexpr int UPL = UNITS / LPR;                        // units per lane
-    static constexpr int RW = (kRW * QB <= LPR) ? kRW : (LPR / QB);   // keeps NV <= LPR
+    static constexpr int ROWBYTES = DIMP * (int)sizeof(T);
+    // row slots per warp per chunk: 8 for short rows (<= 512 B) so a stage stays ~32 KB and the
+    // per-chunk barrier/reduction overhead is spread over more bytes, 4 for long rows
+    static constexpr int RWMAX = (ROWBYTES <= 512) ? 8 : 4;
+    static constexpr int RW = (RWMAX * QB <= LPR) ? RWMAX : (LPR / QB);   // keeps NV <= LPR
     static constexpr int NV = RW * QB;                             // (slot, query) values per lane group
     static constexpr int WARP_ROWS = RW * RPS;                     // rows per warp per chunk
     static constexpr int CHUNK_ROWS = kConsumerWarps * WARP_ROWS;  // rows per shared-memory stage
-    static constexpr int ROWBYTES = DIMP * (int)sizeof(T);
     static constexpr int STAGE_BYTES = CHUNK_ROWS * ROWBYTES;
     static_assert(RW >= 1 && NV <= LPR && UNITS == LPR * UPL, "unsupported scan geometry");
 };
@@ -175,12 +177,21 @@ __global__ void __launch_bounds__(kThreads, 1) match_scan_kernel(const ScanArgs 
     int* my_cnt = wcnt + warp * QB + my_qi;
     const bool is_l2 = (a.metric == FRP_METRIC_L2);
 
+    // |g|^2 of this lane's result row, fetched one chunk ahead so the HBM latency of the
+    // norm load never sits on a chunk's critical path
+    const uint32_t row_in_chunk = warp * WARP_ROWS + my_row_in_warp;
+    auto load_n2 = [&](uint32_t chunk) -> float {
+        const uint64_t r = (uint64_t)chunk * CHUNK_ROWS + row_in_chunk;
+        return (is_l2 && res_lane && chunk < nchunks && r < a.rows) ? __ldg(a.norm2 + r) : 0.f;
+    };
+    float n2_next = load_n2(blockIdx.x);
+
     int s = 0;
     uint32_t phase = 0;
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const uint32_t row_l = c * CHUNK_ROWS + warp * WARP_ROWS + my_row_in_warp;   // this lane's result row
-        float n2 = 0.f;
-        if (is_l2 && res_lane && row_l < a.rows) n2 = __ldg(a.norm2 + row_l);
+        const uint32_t row_l = c * CHUNK_ROWS + row_in_chunk;   // this lane's result row
+        const float n2 = n2_next;
+        n2_next = load_n2(c + gridDim.x);
 
         mbar_wait(&full_bar[s], phase);
         const uint8_t* base = ring + (size_t)s * STAGE_BYTES + (size_t)(warp * WARP_ROWS + sub) * ROWBYTES;
