@@ -12,15 +12,18 @@
 // so each epilogue thread owns ONE query and scans its 256 scores per tile against a
 // running cut, keeping a sorted top-KP list in registers (no cross-thread traffic).
 //
-// Warp roles (192 threads, one CTA per SM, persistent over its gallery tiles):
+// Warp roles (192 or 320 threads, one CTA per SM, persistent over its gallery tiles):
 //   warp 0   TMA producer: queries once, then the gallery ring (cp.async.bulk.tensor
 //            2-D, SWIZZLE_128B, mbarrier complete_tx)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1,
 //            kind::f16, M=128 N=256 K=16), tcgen05.commit -> smem-slot / TMEM-stage
 //            mbarriers
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 of their TMEM lane quadrant, cut test,
+//   warps 2.. epilogue: tcgen05.ld 32x32b.x32 of their TMEM lane quadrant, cut test,
 //            register top-KP insert; double-buffered against the MMA through two
-//            256-column accumulator stages.
+//            256-column accumulator stages.  Four warps (one per quadrant) for long rows;
+//            eight (two per quadrant, 128 columns each, two candidate lists per query
+//            per CTA) for dimp <= 128, where the tensor pipe would otherwise wait for
+//            the scan.
 // Batches of 129..256 (any even number of 128-query groups) run as clusters of two CTAs
 // that stream the SAME gallery tiles: each CTA fetches half of every tile and
 // TMA-multicasts it into both CTAs' shared memory (UTMALDG.2D.MULTICAST), the smem slot
@@ -47,7 +50,9 @@ constexpr int kTileM = 128;        // queries per CTA
 constexpr int kTileN = 256;        // gallery rows per MMA tile
 constexpr int kBlockK = 64;        // halfs per K block (128-byte swizzle span)
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+// LPC ("lists per CTA", template parameter) = epilogue warps per TMEM lane quadrant: 1 -> 4
+// epilogue warps that scan whole tiles, 2 -> 8 warps that scan half a tile each.
+constexpr int threads_for(int lpc) { return 64 + 128 * lpc; }
 constexpr int kABlockBytes = kTileM * kBlockK * 2;   // 16 KB
 constexpr int kBStageBytes = kTileN * kBlockK * 2;   // 32 KB
 constexpr int kMaxStages = 6;
@@ -116,6 +121,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
 // start address >> 4 | LBO = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
@@ -153,8 +163,8 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
         : "memory");
 }
 
-template <int KP, bool IS_L2, int CS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int KP, bool IS_L2, int CS, int LPC>
+__global__ void __launch_bounds__(threads_for(LPC), 1)
 match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                   const __grid_constant__ CUtensorMap tmap_gh, const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -187,9 +197,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // a smem slot is free when the MMAs of EVERY CTA of the cluster have retired (the
         // peer multicasts into this CTA's slot too)
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * LPC); }
         mbar_init(afull_bar, 1);
-        for (int s = 0; s < kNormSlots; ++s) { mbar_init(&nfull_bar[s], 1); mbar_init(&nempty_bar[s], 4); }
+        for (int s = 0; s < kNormSlots; ++s) { mbar_init(&nfull_bar[s], 1); mbar_init(&nempty_bar[s], 4 * LPC); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -272,8 +282,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
     } else {
-        // ================= epilogue: one query per thread =================
+        // ================= epilogue: one query per thread, half a tile per warp =================
+        // Eight warps: warp w may only touch TMEM lane quadrant w % 4, so two warps share a
+        // quadrant (= the same 32 queries) and split the tile's 256 columns.  Two warps per
+        // scheduler hide each other's tcgen05.ld / shared-memory / FMNMX latencies; each
+        // keeps its own top-KP list, so a CTA emits two lists per query.
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        constexpr int kEpiCols = kTileN / LPC;          // tile columns scanned by one epilogue warp
+        const int half = (warp - 2) >> 2;               // which column range of every tile
         const int q = qgroup * kTileM + quad * 32 + lane;
         const bool valid_q = q < a.B;
         const float ninf = __int_as_float(0xff800000);
@@ -283,18 +299,19 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         uint32_t lr[KP];
 #pragma unroll
         for (int p = 0; p < KP; ++p) { ls[p] = ninf; lr[p] = 0xffffffffu; }
+        const uint32_t norm_u32 = smem_u32(norm_ring);
 
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t as = i & 1;
-            const uint32_t row0 = (blockIdx.x + i * gridDim.x) * kTileN;
+            const uint32_t row0 = (blockIdx.x + i * gridDim.x) * kTileN + half * kEpiCols;
             const uint32_t ns = i % kNormSlots;
-            const float* nsm = norm_ring + ns * kTileN;
+            const uint32_t nsm = norm_u32 + (ns * kTileN + half * kEpiCols) * 4;
             if (IS_L2) mbar_wait(&nfull_bar[ns], (i / kNormSlots) & 1);
             mbar_wait(&tfull_bar[as], (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + half * kEpiCols;
 #pragma unroll 1
-            for (int c = 0; c < kTileN; c += 32) {
+            for (int c = 0; c < kEpiCols; c += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c, v);
                 tmem_ld_wait();
@@ -303,7 +320,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     // s = 2 g.q - |g|^2 ; every lane reads the same shared-memory words (broadcast)
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 n4 = *reinterpret_cast<const float4*>(nsm + c + j);
+                        const float4 n4 = lds_f4(nsm + (c + j) * 4);
                         sv[j] = fmaf(2.f, __uint_as_float(v[j]), -n4.x);
                         sv[j + 1] = fmaf(2.f, __uint_as_float(v[j + 1]), -n4.y);
                         sv[j + 2] = fmaf(2.f, __uint_as_float(v[j + 2]), -n4.z);
@@ -314,10 +331,17 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
                 }
                 // one branch per 32 scores: a per-element branch costs a convergence
-                // barrier (BSSY/BSYNC) each and made the epilogue the bottleneck
-                float mx = sv[0];
+                // barrier (BSSY/BSYNC) each and made the epilogue the bottleneck.  Four
+                // independent max chains keep the dependent-issue depth at 8 + 2.
+                float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sv[j]);
+                for (int j = 4; j < 32; j += 4) {
+                    m0 = fmaxf(m0, sv[j]);
+                    m1 = fmaxf(m1, sv[j + 1]);
+                    m2 = fmaxf(m2, sv[j + 2]);
+                    m3 = fmaxf(m3, sv[j + 3]);
+                }
+                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 if (mx >= cut) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -351,7 +375,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
         if (valid_q) {
-            uint64_t* out = a.cand + ((size_t)q * gridDim.x + blockIdx.x) * KP;
+            uint64_t* out = a.cand + ((size_t)q * (gridDim.x * LPC) + blockIdx.x * LPC + half) * KP;
 #pragma unroll
             for (int p = 0; p < KP; ++p) out[p] = (lr[p] != 0xffffffffu) ? make_key(ls[p], lr[p]) : 0ull;
         }
@@ -427,13 +451,26 @@ bool gemm_supported(const frp_gallery* g) {
 
 static int gemm_groups(int B) { return (B + kTileM - 1) / kTileM; }
 
+// Short rows (dimp <= 128) leave only ~1 000 tensor-pipe cycles per tile, less than one warp
+// per scheduler needs for the 256-column scan: use two epilogue warps per quadrant there.
+// Long rows hide the scan behind the MMAs already; the extra warps only cost power.
+// FRP_GEMM_LPC=1|2 overrides (A/B measurements).
+static int gemm_lpc(const frp_gallery* g) {
+    static const int forced = []() {
+        const char* e = getenv("FRP_GEMM_LPC");
+        return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }();
+    if (forced) return forced;
+    return g->dimp <= 128 ? 2 : 1;
+}
+
 int gemm_num_lists(const frp_gallery* g, int B) {
     const int groups = gemm_groups(B);
     int per = g->sm_count / groups;
     if (per < 1) per = 1;
     const uint64_t ntiles = (g->rows + kTileN - 1) / kTileN;
     if ((uint64_t)per > ntiles) per = (int)ntiles;
-    return per;
+    return per * gemm_lpc(g);
 }
 
 int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP, uint64_t* cand,
@@ -465,11 +502,12 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     a.metric = g->metric;
     const size_t smem = 1024 + (size_t)nkb * kABlockBytes + (size_t)stages * kBStageBytes + 256 +
                         (l2 ? kNormRingBytes : 0);
-    dim3 grid(nlists, groups);
+    const int lpc = gemm_lpc(g);
+    dim3 grid(nlists / lpc, groups);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads_for(lpc));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -480,28 +518,31 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t le = cudaSuccess;
-#define FRP_GEMM_LAUNCH(KP_, L2_, CS_)                                                                   \
+#define FRP_GEMM_LAUNCH(KP_, L2_, CS_, LPC_)                                                             \
     {                                                                                                    \
         static thread_local size_t configured = 0;                                                       \
         if (configured < smem) {                                                                         \
-            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_, CS_>,                              \
+            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_, CS_, LPC_>,                        \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
             configured = smem;                                                                           \
         }                                                                                                \
-        le = cudaLaunchKernelEx(&cfg, match_gemm_kernel<KP_, L2_, CS_>, tq, tg, tgh, a);                 \
+        le = cudaLaunchKernelEx(&cfg, match_gemm_kernel<KP_, L2_, CS_, LPC_>, tq, tg, tgh, a);           \
     }
-    const int key =(KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (cs == 2 ? 1 : 0);
+#define FRP_GEMM_CASES(LPC_)                                 \
+    switch (key) {                                           \
+        case 0: FRP_GEMM_LAUNCH(16, false, 1, LPC_) break;   \
+        case 1: FRP_GEMM_LAUNCH(16, false, 2, LPC_) break;   \
+        case 2: FRP_GEMM_LAUNCH(16, true, 1, LPC_) break;    \
+        case 3: FRP_GEMM_LAUNCH(16, true, 2, LPC_) break;    \
+        case 4: FRP_GEMM_LAUNCH(32, false, 1, LPC_) break;   \
+        case 5: FRP_GEMM_LAUNCH(32, false, 2, LPC_) break;   \
+        case 6: FRP_GEMM_LAUNCH(32, true, 1, LPC_) break;    \
+        default: FRP_GEMM_LAUNCH(32, true, 2, LPC_) break;   \
+    }
+    const int key = (KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (cs == 2 ? 1 : 0);
     if (KP != 16 && KP != 32) { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
-    switch (key) {
-        case 0: FRP_GEMM_LAUNCH(16, false, 1) break;
-        case 1: FRP_GEMM_LAUNCH(16, false, 2) break;
-        case 2: FRP_GEMM_LAUNCH(16, true, 1) break;
-        case 3: FRP_GEMM_LAUNCH(16, true, 2) break;
-        case 4: FRP_GEMM_LAUNCH(32, false, 1) break;
-        case 5: FRP_GEMM_LAUNCH(32, false, 2) break;
-        case 6: FRP_GEMM_LAUNCH(32, true, 1) break;
-        default: FRP_GEMM_LAUNCH(32, true, 2) break;
-    }
+    if (lpc == 2) FRP_GEMM_CASES(2) else FRP_GEMM_CASES(1)
+#undef FRP_GEMM_CASES
 #undef FRP_GEMM_LAUNCH
     if (le != cudaSuccess) {
         set_error("match_gemm launch failed: %s", cudaGetErrorString(le));
