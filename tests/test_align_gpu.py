@@ -79,6 +79,40 @@ def test_fully_outside_and_degenerate():
     assert align.norm_crop_batch(frames, [], lmk=np.zeros((0, 5, 2), np.float32))[0].shape == (0, 3, 112, 112)
 
 
+def test_caller_matrices_all_sign_patterns():
+    """Caller-supplied 2x3 maps: every rotation quadrant, reflections, shear, scales 0.2-4 and
+    translations that push part (or all, up to the int16 saturation of cv::remap) of the
+    footprint outside the frame.  The per-crop staging plan picks the box corner from the
+    signs of the inverse map; all four sign patterns of each row are exercised."""
+    H, W = 480, 640
+    frames = o.synth_frames(2, H, W, seed=61)
+    rng = np.random.default_rng(62)
+    Ms, fi = [], []
+    for k in range(160):
+        th = (k % 16) * (2 * np.pi / 16) + rng.uniform(-0.15, 0.15)
+        sc = float(rng.choice([0.2, 0.5, 0.8, 1.0, 1.3, 2.0, 3.1, 4.0]))     # output px per source px
+        A = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]) * sc
+        if k % 5 == 1:
+            A = A @ np.array([[1.0, 0.0], [0.0, -1.0]])      # reflection
+        if k % 5 == 2:
+            A = A @ np.array([[1.0, 0.35], [0.0, 1.0]])      # shear
+        if k % 5 == 3:
+            A = A @ np.diag([1.0, 0.6])                      # anisotropic
+        c = np.array([rng.uniform(-40, W + 40), rng.uniform(-40, H + 40)])    # source point mapped to the crop centre
+        if k % 40 == 7:
+            c = np.array([31000.0, -31000.0])                 # beyond the int16 range of the xy map
+        t = np.array([56.0, 56.0]) - A @ c
+        Ms.append(np.hstack([A, t[:, None]]))
+        fi.append(k % 2)
+    M = np.stack(Ms)
+    blob, al = align.norm_crop_batch(frames, fi, M=M, return_aligned=True)
+    wal, wbl = _oracle_batch(frames, fi, M)
+    bad = [i for i in range(len(fi)) if not np.array_equal(al[i], wal[i])]
+    assert not bad, bad
+    assert np.array_equal(blob, wbl)
+    assert sum(int(a.any()) for a in al) > 100      # most crops do show the frame
+
+
 def test_device_path_many_crops():
     """BASELINE.json configs[3] at full size: 4 096 detections from 16 1080p frames."""
     import torch
@@ -96,7 +130,7 @@ def test_device_path_many_crops():
     before = frp_b200.kernel_launches()
     align.norm_crop_batch_device(d_fr, F, H, W, 3 * W, d_fi, d_lm, n, out, out_al, stream=st)
     torch.cuda.synchronize()
-    assert frp_b200.kernel_launches() == before + 1
+    assert frp_b200.kernel_launches() == before + 2      # align_plan_kernel + align_kernel
     al = out_al.cpu().numpy()
     blob = out.cpu().numpy()
     sel = np.random.default_rng(0).choice(n, 64, replace=False)
