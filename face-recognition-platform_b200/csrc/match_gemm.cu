@@ -31,8 +31,8 @@
 // L2 metric: |g|^2 of each tile reaches the epilogue through a 4-slot bulk-copy ring.
 // Output contract is the scan kernel's: cand[B][nlists][KP] u64 keys.
 //
-// Not taken this round: the cta_group::2 (M=256 pair MMA) form of the same kernel; a first
-// attempt faulted in its barrier/TMA plumbing and was reverted ("next").
+// 512-d rows with an even number of groups use match_gemm_pair_kernel instead: the same
+// pipeline with cta_group::2 (M=256) MMAs issued by the leader CTA of the pair (below).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -56,6 +56,7 @@ constexpr int threads_for(int lpc) { return 64 + 128 * lpc; }
 constexpr int kABlockBytes = kTileM * kBlockK * 2;   // 16 KB
 constexpr int kBStageBytes = kTileN * kBlockK * 2;   // 32 KB
 constexpr int kMaxStages = 6;
+constexpr int kMaxPairStages = 12;                  // CTA-pair kernel: half-tile (16 KB) slots
 constexpr int kAccCols = kTileN;                     // fp32 accumulator columns per stage
 constexpr uint32_t kTmemCols = 512;
 constexpr int kNormSlots = 4;                        // L2 metric: |g|^2 tiles in flight
@@ -148,6 +149,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
                                                uint16_t mask) {
     asm volatile(
@@ -161,6 +170,115 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
         ::"r"(smem_u32(bar)), "h"(mask)
         : "memory");
+}
+
+// ---- epilogue warps (shared by the one-CTA and the CTA-pair kernels) ------------------
+// list / nlist: this CTA's tile stream (tiles list, list + nlist, ...) and candidate-list slot.
+template <int KP, bool IS_L2, int LPC, bool PAIR>
+__device__ __forceinline__ void epilogue_warps(const GemmArgs& a, const int warp, const int lane, const int qgroup,
+                                               const uint32_t list, const uint32_t nlist, const uint32_t my_tiles,
+                                               const uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                               uint64_t* nfull_bar, uint64_t* nempty_bar, float* norm_ring,
+                                               const uint32_t tempty_leader) {
+    // ================= epilogue: one query per thread, half a tile per warp =================
+    // Eight warps: warp w may only touch TMEM lane quadrant w % 4, so two warps share a
+    // quadrant (= the same 32 queries) and split the tile's 256 columns.  Two warps per
+    // scheduler hide each other's tcgen05.ld / shared-memory / FMNMX latencies; each
+    // keeps its own top-KP list, so a CTA emits two lists per query.
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    constexpr int kEpiCols = kTileN / LPC;          // tile columns scanned by one epilogue warp
+    const int half = (warp - 2) >> 2;               // which column range of every tile
+    const int q = qgroup * kTileM + quad * 32 + lane;
+    const bool valid_q = q < a.B;
+    const float ninf = __int_as_float(0xff800000);
+    float cut0 = valid_q ? a.qp[q].cut0 : __int_as_float(0x7f800000);
+    float cut = cut0;
+    float ls[KP];
+    uint32_t lr[KP];
+#pragma unroll
+    for (int p = 0; p < KP; ++p) { ls[p] = ninf; lr[p] = 0xffffffffu; }
+    const uint32_t norm_u32 = smem_u32(norm_ring);
+
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t as = i & 1;
+        const uint32_t row0 = (list + i * nlist) * kTileN + half * kEpiCols;
+        const uint32_t ns = i % kNormSlots;
+        const uint32_t nsm = norm_u32 + (ns * kTileN + half * kEpiCols) * 4;
+        if (IS_L2) mbar_wait(&nfull_bar[ns], (i / kNormSlots) & 1);
+        mbar_wait(&tfull_bar[as], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + half * kEpiCols;
+#pragma unroll 1
+        for (int c = 0; c < kEpiCols; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c, v);
+            tmem_ld_wait();
+            float sv[32];
+            if (IS_L2) {
+                // s = 2 g.q - |g|^2 ; every lane reads the same shared-memory words (broadcast)
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 n4 = lds_f4(nsm + (c + j) * 4);
+                    sv[j] = fmaf(2.f, __uint_as_float(v[j]), -n4.x);
+                    sv[j + 1] = fmaf(2.f, __uint_as_float(v[j + 1]), -n4.y);
+                    sv[j + 2] = fmaf(2.f, __uint_as_float(v[j + 2]), -n4.z);
+                    sv[j + 3] = fmaf(2.f, __uint_as_float(v[j + 3]), -n4.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
+            }
+            // one branch per 32 scores: a per-element branch costs a convergence
+            // barrier (BSSY/BSYNC) each and made the epilogue the bottleneck.  Four
+            // independent max chains keep the dependent-issue depth at 8 + 2.
+            float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
+#pragma unroll
+            for (int j = 4; j < 32; j += 4) {
+                m0 = fmaxf(m0, sv[j]);
+                m1 = fmaxf(m1, sv[j + 1]);
+                m2 = fmaxf(m2, sv[j + 2]);
+                m3 = fmaxf(m3, sv[j + 3]);
+            }
+            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (mx >= cut) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = sv[j];
+                    const uint32_t row = row0 + c + j;
+                    if (s >= cut && row < a.rows) {
+                        if (a.alive[row]) {
+                            float cs = s;
+                            uint32_t cr = row;
+#pragma unroll
+                            for (int p = 0; p < KP; ++p) {
+                                const bool gt = cs > ls[p];
+                                const float ts = gt ? ls[p] : cs;
+                                const uint32_t tr = gt ? lr[p] : cr;
+                                ls[p] = gt ? cs : ls[p];
+                                lr[p] = gt ? cr : lr[p];
+                                cs = ts;
+                                cr = tr;
+                            }
+                            cut = fmaxf(cut0, ls[KP - 1]);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            // PAIR: the MMA issuer lives in the leader CTA and waits for both CTAs' scans
+            if (PAIR) mbar_arrive_cluster(tempty_leader + as * 8);
+            else mbar_arrive(&tempty_bar[as]);
+            if (IS_L2) mbar_arrive(&nempty_bar[ns]);
+        }
+    }
+    if (valid_q) {
+        uint64_t* out = a.cand + ((size_t)q * (nlist * LPC) + list * LPC + half) * KP;
+#pragma unroll
+        for (int p = 0; p < KP; ++p) out[p] = (lr[p] != 0xffffffffu) ? make_key(ls[p], lr[p]) : 0ull;
+    }
 }
 
 template <int KP, bool IS_L2, int CS, int LPC>
@@ -282,103 +400,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
     } else {
-        // ================= epilogue: one query per thread, half a tile per warp =================
-        // Eight warps: warp w may only touch TMEM lane quadrant w % 4, so two warps share a
-        // quadrant (= the same 32 queries) and split the tile's 256 columns.  Two warps per
-        // scheduler hide each other's tcgen05.ld / shared-memory / FMNMX latencies; each
-        // keeps its own top-KP list, so a CTA emits two lists per query.
-        const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-        constexpr int kEpiCols = kTileN / LPC;          // tile columns scanned by one epilogue warp
-        const int half = (warp - 2) >> 2;               // which column range of every tile
-        const int q = qgroup * kTileM + quad * 32 + lane;
-        const bool valid_q = q < a.B;
-        const float ninf = __int_as_float(0xff800000);
-        float cut0 = valid_q ? a.qp[q].cut0 : __int_as_float(0x7f800000);
-        float cut = cut0;
-        float ls[KP];
-        uint32_t lr[KP];
-#pragma unroll
-        for (int p = 0; p < KP; ++p) { ls[p] = ninf; lr[p] = 0xffffffffu; }
-        const uint32_t norm_u32 = smem_u32(norm_ring);
-
-        for (uint32_t i = 0; i < my_tiles; ++i) {
-            const uint32_t as = i & 1;
-            const uint32_t row0 = (blockIdx.x + i * gridDim.x) * kTileN + half * kEpiCols;
-            const uint32_t ns = i % kNormSlots;
-            const uint32_t nsm = norm_u32 + (ns * kTileN + half * kEpiCols) * 4;
-            if (IS_L2) mbar_wait(&nfull_bar[ns], (i / kNormSlots) & 1);
-            mbar_wait(&tfull_bar[as], (i >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + half * kEpiCols;
-#pragma unroll 1
-            for (int c = 0; c < kEpiCols; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c, v);
-                tmem_ld_wait();
-                float sv[32];
-                if (IS_L2) {
-                    // s = 2 g.q - |g|^2 ; every lane reads the same shared-memory words (broadcast)
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 n4 = lds_f4(nsm + (c + j) * 4);
-                        sv[j] = fmaf(2.f, __uint_as_float(v[j]), -n4.x);
-                        sv[j + 1] = fmaf(2.f, __uint_as_float(v[j + 1]), -n4.y);
-                        sv[j + 2] = fmaf(2.f, __uint_as_float(v[j + 2]), -n4.z);
-                        sv[j + 3] = fmaf(2.f, __uint_as_float(v[j + 3]), -n4.w);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
-                }
-                // one branch per 32 scores: a per-element branch costs a convergence
-                // barrier (BSSY/BSYNC) each and made the epilogue the bottleneck.  Four
-                // independent max chains keep the dependent-issue depth at 8 + 2.
-                float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
-#pragma unroll
-                for (int j = 4; j < 32; j += 4) {
-                    m0 = fmaxf(m0, sv[j]);
-                    m1 = fmaxf(m1, sv[j + 1]);
-                    m2 = fmaxf(m2, sv[j + 2]);
-                    m3 = fmaxf(m3, sv[j + 3]);
-                }
-                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                if (mx >= cut) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = sv[j];
-                        const uint32_t row = row0 + c + j;
-                        if (s >= cut && row < a.rows) {
-                            if (a.alive[row]) {
-                                float cs = s;
-                                uint32_t cr = row;
-#pragma unroll
-                                for (int p = 0; p < KP; ++p) {
-                                    const bool gt = cs > ls[p];
-                                    const float ts = gt ? ls[p] : cs;
-                                    const uint32_t tr = gt ? lr[p] : cr;
-                                    ls[p] = gt ? cs : ls[p];
-                                    lr[p] = gt ? cr : lr[p];
-                                    cs = ts;
-                                    cr = tr;
-                                }
-                                cut = fmaxf(cut0, ls[KP - 1]);
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty_bar[as]);
-                if (IS_L2) mbar_arrive(&nempty_bar[ns]);
-            }
-        }
-        if (valid_q) {
-            uint64_t* out = a.cand + ((size_t)q * (gridDim.x * LPC) + blockIdx.x * LPC + half) * KP;
-#pragma unroll
-            for (int p = 0; p < KP; ++p) out[p] = (lr[p] != 0xffffffffu) ? make_key(ls[p], lr[p]) : 0ull;
-        }
+        epilogue_warps<KP, IS_L2, LPC, false>(a, warp, lane, qgroup, blockIdx.x, gridDim.x, my_tiles, tmem_base,
+                                              tfull_bar, tempty_bar, nfull_bar, nempty_bar, norm_ring, 0u);
     }
 
     tc_fence_before();
@@ -389,6 +412,177 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------
+// The two 128-query groups of a 256-query batch run as one CTA pair issuing M=256 MMAs:
+// each CTA keeps its own 128 queries (A) and stages only ITS half of every gallery tile
+// (128 of the 256 rows, B) — the tensor cores of both SMs read both halves, so the
+// shared-memory traffic per MMA halves and no multicast copy is needed.  Plumbing
+// (as CUTLASS' 2-SM kernels do it): both CTAs' TMA loads complete on the LEADER's full
+// barrier (cp.async.bulk.tensor ... cta_group::2), only the leader's warp 1 issues
+// tcgen05.mma.cta_group::2, its commits are multicast to both CTAs' barriers, and the
+// peer's epilogue warps release the accumulator stage on the leader's barrier.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// dst in this CTA's shared memory, completion bytes on the barrier at cluster address bar_caddr
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_caddr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_caddr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+constexpr int kBHalfBytes = kBStageBytes / 2;      // 128 gallery rows x 64 halfs
+// kind::f16 instruction descriptor for the pair: M = 256 (128 per CTA), N = 256
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)((2 * kTileM) >> 4) << 24);
+
+template <int KP, bool IS_L2, int LPC>
+__global__ void __launch_bounds__(threads_for(LPC), 1)
+match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_gh,
+                       const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)a.nkb * kABlockBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)a.stages * kBHalfBytes);
+    uint64_t* full_bar = bars;                       // [kMaxPairStages]   (used in the leader)
+    uint64_t* empty_bar = bars + kMaxPairStages;     // [kMaxPairStages]
+    uint64_t* tfull_bar = bars + 2 * kMaxPairStages;       // [2]
+    uint64_t* tempty_bar = bars + 2 * kMaxPairStages + 2;  // [2]          (used in the leader)
+    uint64_t* afull_bar = bars + 2 * kMaxPairStages + 4;   // [1]          (used in the leader)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxPairStages + 5);
+    uint64_t* nfull_bar = bars + 2 * kMaxPairStages + 6;   // [kNormSlots]
+    uint64_t* nempty_bar = nfull_bar + kNormSlots;         // [kNormSlots]
+    float* norm_ring = reinterpret_cast<float*>(bars + 2 * kMaxPairStages + 6 + 2 * kNormSlots + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();        // 0 = leader
+    const int qgroup = blockIdx.y * 2 + (int)crank;
+    const uint32_t list = blockIdx.x >> 1, nlist = gridDim.x >> 1;
+    const uint32_t my_tiles = (a.ntiles > list) ? (a.ntiles - list + nlist - 1) / nlist : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_gh);
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * 4 * LPC); }
+        mbar_init(afull_bar, 1);
+        for (int s = 0; s < kNormSlots; ++s) { mbar_init(&nfull_bar[s], 1); mbar_init(&nempty_bar[s], 4 * LPC); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' barriers exist before anything is signalled
+    if (warp == 1) tmem_alloc2(tmem_ptr, kTmemCols);     // the same warp in both CTAs
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    // cluster addresses of the leader's barriers
+    const uint32_t full_leader = mapa_u32(smem_u32(full_bar), 0);
+    const uint32_t afull_leader = mapa_u32(smem_u32(afull_bar), 0);
+    const uint32_t tempty_leader = mapa_u32(smem_u32(tempty_bar), 0);
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            if (crank == 0) mbar_expect_tx(afull_bar, 2u * (uint32_t)a.nkb * kABlockBytes);
+            for (int kb = 0; kb < a.nkb; ++kb)
+                tma_load_2d_2sm(&tmap_q, afull_leader, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK,
+                                qgroup * kTileM);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const int row0 = (int)((list + i * nlist) * kTileN);
+            if (IS_L2) {
+                const uint32_t ns = i % kNormSlots;
+                mbar_wait(&nempty_bar[ns], ((i / kNormSlots) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(&nfull_bar[ns], kTileN * 4);
+                    bulk_g2s(norm_ring + ns * kTileN, a.norm2 + row0, kTileN * 4, &nfull_bar[ns]);
+                }
+                __syncwarp();
+            }
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);      // the pair's MMAs on this slot have retired
+                if (lane == 0) {
+                    if (crank == 0) mbar_expect_tx(&full_bar[s], kBStageBytes);     // both halves
+                    tma_load_2d_2sm(&tmap_gh, full_leader + (uint32_t)s * 8, smem_b + (size_t)s * kBHalfBytes,
+                                    kb * kBlockK, row0 + (int)crank * (kTileN / 2));
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (crank == 0) {
+            mbar_wait(afull_bar, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t as = i & 1;
+                mbar_wait(&tempty_bar[as], ((i >> 1) & 1) ^ 1);     // both CTAs drained this TMEM stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kAccCols;
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);                    // both halves of the K block landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = a_base + (uint32_t)kb * kABlockBytes;
+                        const uint32_t b_addr = b_base + (uint32_t)s * kBHalfBytes;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK * 2);
+                            const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
+                            umma_f16_2(tmem_d, adesc, bdesc, kIdescPair, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit2_mc(&empty_bar[s], (uint16_t)0x3);              // slot free in both CTAs
+                        if (kb == a.nkb - 1) umma_commit2_mc(&tfull_bar[as], (uint16_t)0x3);   // accumulators ready
+                    }
+                    __syncwarp();
+                    if (++s == a.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        epilogue_warps<KP, IS_L2, LPC, true>(a, warp, lane, qgroup, list, nlist, my_tiles, tmem_base, tfull_bar,
+                                             tempty_bar, nfull_bar, nempty_bar, norm_ring, tempty_leader);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // the peer may still signal this CTA's barriers / read its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, kTmemCols);
     }
 }
 
@@ -443,6 +637,17 @@ static const bool g_gemm_no_cluster = []() {
     const char* e = getenv("FRP_GEMM_NO_CLUSTER");
     return e && e[0] == '1';
 }();
+
+// The cta_group::2 CTA-pair kernel serves even group counts of 512-d rows (measured 2.10 vs
+// 2.17 ms on the 10 M x 512 headline, 1.43 vs 1.48 ms at B = 1 024 x 2 M); shorter rows are
+// paced by the epilogue hand-off and run faster on the multicast kernel (256-d: 0.42 vs
+// 0.47 ms, 128-d L2: 0.246 vs 0.293 ms).  FRP_GEMM_PAIR=0|1 forces it
+// off / on for every dimension (A/B measurements).
+static const int g_gemm_pair = []() {
+    const char* e = getenv("FRP_GEMM_PAIR");
+    return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+}();
+static bool use_pair_kernel(const frp_gallery* g) { return g_gemm_pair < 0 ? g->dimp >= 512 : g_gemm_pair == 1; }
 
 bool gemm_supported(const frp_gallery* g) {
     return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
@@ -518,6 +723,49 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t le = cudaSuccess;
+    if (cs == 2 && use_pair_kernel(g)) {
+        // CTA-pair kernel: cluster (2,1,1) = the two query groups of one 256-query slab
+        int pst = (227 * 1024 - 2048 - nkb * kABlockBytes - 512 - (l2 ? kNormRingBytes : 0)) / kBHalfBytes;
+        if (pst > kMaxPairStages) pst = kMaxPairStages;
+        if (pst < 2) { set_error("match_gemm: not enough shared memory for dimp=%d", g->dimp); return FRP_E_UNSUPPORTED; }
+        a.stages = pst;
+        const size_t psmem = 1024 + (size_t)nkb * kABlockBytes + (size_t)pst * kBHalfBytes + 512 +
+                             (l2 ? kNormRingBytes : 0);
+        cfg.gridDim = dim3(2 * (nlists / lpc), groups / 2);
+        cfg.dynamicSmemBytes = psmem;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+#define FRP_PAIR_LAUNCH(KP_, L2_, LPC_)                                                                  \
+    {                                                                                                    \
+        static thread_local size_t configured = 0;                                                       \
+        if (configured < psmem) {                                                                        \
+            FRP_CUDA(cudaFuncSetAttribute(match_gemm_pair_kernel<KP_, L2_, LPC_>,                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));     \
+            configured = psmem;                                                                          \
+        }                                                                                                \
+        le = cudaLaunchKernelEx(&cfg, match_gemm_pair_kernel<KP_, L2_, LPC_>, tq, tgh, a);               \
+    }
+        if (KP != 16 && KP != 32) { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
+        const int pkey = (KP == 32 ? 4 : 0) | (l2 ? 2 : 0) | (lpc == 2 ? 1 : 0);
+        switch (pkey) {
+            case 0: FRP_PAIR_LAUNCH(16, false, 1) break;
+            case 1: FRP_PAIR_LAUNCH(16, false, 2) break;
+            case 2: FRP_PAIR_LAUNCH(16, true, 1) break;
+            case 3: FRP_PAIR_LAUNCH(16, true, 2) break;
+            case 4: FRP_PAIR_LAUNCH(32, false, 1) break;
+            case 5: FRP_PAIR_LAUNCH(32, false, 2) break;
+            case 6: FRP_PAIR_LAUNCH(32, true, 1) break;
+            default: FRP_PAIR_LAUNCH(32, true, 2) break;
+        }
+#undef FRP_PAIR_LAUNCH
+        if (le != cudaSuccess) {
+            set_error("match_gemm (pair) launch failed: %s", cudaGetErrorString(le));
+            cudaGetLastError();
+            return FRP_E_CUDA;
+        }
+        FRP_CHECK_LAUNCH();
+        return FRP_OK;
+    }
 #define FRP_GEMM_LAUNCH(KP_, L2_, CS_, LPC_)                                                             \
     {                                                                                                    \
         static thread_local size_t configured = 0;                                                       \
