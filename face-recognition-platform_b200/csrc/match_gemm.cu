@@ -31,7 +31,7 @@
 // L2 metric: |g|^2 of each tile reaches the epilogue through a 4-slot bulk-copy ring.
 // Output contract is the scan kernel's: cand[B][nlists][KP] u64 keys.
 //
-// 512-d rows with an even number of groups use match_gemm_pair_kernel instead: the same
+// Rows >= 256-d with an even number of groups use match_gemm_pair_kernel instead: the same
 // pipeline with cta_group::2 (M=256) MMAs issued by the leader CTA of the pair (below).
 #include <cuda.h>
 #include <stdlib.h>
@@ -154,8 +154,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
     return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default (cta-scope release) semantics as
+// in CUTLASS' ClusterBarrier::arrive: what the arrival orders here is TMEM traffic, which the
+// tcgen05 fences around it cover; a cluster-scope release costs a full memory barrier
+// (SASS ERRBAR, 30 % of the epilogue's stall samples when it was tried).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
                                                uint16_t mask) {
@@ -638,16 +642,15 @@ static const bool g_gemm_no_cluster = []() {
     return e && e[0] == '1';
 }();
 
-// The cta_group::2 CTA-pair kernel serves even group counts of 512-d rows (measured 2.10 vs
-// 2.17 ms on the 10 M x 512 headline, 1.43 vs 1.48 ms at B = 1 024 x 2 M); shorter rows are
-// paced by the epilogue hand-off and run faster on the multicast kernel (256-d: 0.42 vs
-// 0.47 ms, 128-d L2: 0.246 vs 0.293 ms).  FRP_GEMM_PAIR=0|1 forces it
+// The cta_group::2 CTA-pair kernel serves even group counts of rows >= 256-d (4 M rows, batch
+// 256: 512-d 0.822 vs 0.871 ms, 256-d 0.417 vs 0.423 ms); 128-d rows are paced by the
+// epilogue and run the same or slightly faster on the multicast kernel (0.229 vs 0.232 ms).  FRP_GEMM_PAIR=0|1 forces it
 // off / on for every dimension (A/B measurements).
 static const int g_gemm_pair = []() {
     const char* e = getenv("FRP_GEMM_PAIR");
     return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
 }();
-static bool use_pair_kernel(const frp_gallery* g) { return g_gemm_pair < 0 ? g->dimp >= 512 : g_gemm_pair == 1; }
+static bool use_pair_kernel(const frp_gallery* g) { return g_gemm_pair < 0 ? g->dimp >= 256 : g_gemm_pair == 1; }
 
 bool gemm_supported(const frp_gallery* g) {
     return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
