@@ -299,6 +299,47 @@ def test_tcgen05_path_other_dims(dim, metric):
         assert np.abs(a[1][bq, :a[2][bq]] - S[bq][got]).max(initial=0) < TIGHT
 
 
+@pytest.mark.parametrize("B", [200, 256, 512])
+@pytest.mark.parametrize("dim,metric", [(256, METRIC_L2), (512, METRIC_L2), (384, METRIC_COS), (256, METRIC_COS)])
+def test_tcgen05_pair_kernel_dims_metrics(B, dim, metric):
+    """Even numbers of 128-query groups on rows >= 256-d run the cta_group::2 CTA-pair kernel
+    (both metrics: the L2 form also exercises its per-CTA norm ring); a ragged last tile, a
+    partly filled second group (B = 200) and tombstones included."""
+    rng = np.random.default_rng(1000 * dim + B)
+    N, k = 20_011, 9
+    G = rng.normal(0, 0.06, (N, dim)).astype(np.float32)
+    Q = G[rng.integers(0, N, B)] + rng.normal(0, 0.03, (B, dim)).astype(np.float32)
+    gal = Gallery(dim, metric)
+    gal.append(G)
+    dead = rng.integers(0, N, 7)
+    for r in dead:
+        gal.remove(int(r))
+    if metric == METRIC_L2:
+        S = np.stack([np.linalg.norm(G.astype(np.float64) - q.astype(np.float64), axis=1) for q in Q[:8]])
+        tau = float(np.sort(S[0])[30])
+    else:
+        S = o.cosine_scores(G, Q[:8])
+        tau = float(np.sort(S[0])[-30])
+    a = gal.match(Q, tau, k, MATCH_FORCE_GEMM)
+    assert frp_b200.last_match_path() == "gemm_tcgen05"
+    assert np.all(a[3] == 0)
+    b = gal.match(Q, tau, k, MATCH_FORCE_SCAN)
+    c = gal.match(Q, tau, k, MATCH_FORCE_EXACT)
+    for r in (b, c):
+        assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1], equal_nan=True) and np.array_equal(a[2], r[2])
+    assert not np.isin(a[0][a[0] >= 0], dead).any()
+    for bq in range(8):
+        got = a[0][bq, :a[2][bq]]
+        assert np.abs(a[1][bq, :a[2][bq]] - S[bq][got]).max(initial=0) < TIGHT
+        live = np.ones(N, bool)
+        live[dead] = False
+        order = np.argsort(S[bq] if metric == METRIC_L2 else -S[bq], kind="stable")
+        order = order[live[order]]
+        ok = (S[bq][order] <= tau) if metric == METRIC_L2 else (S[bq][order] >= tau)
+        want = order[ok][:k]
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("dim", [64, 100, 128, 256, 384, 512])
 @pytest.mark.parametrize("metric", [METRIC_L2, METRIC_COS])
 def test_dims_and_metrics(dim, metric):
