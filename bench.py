@@ -398,6 +398,10 @@ def run_ours(args):
     extras = {}
     if world == 1 and not args.no_extras and rank == 0:
         extras = side_measurements(args, frp, torch, gal, queries, pk, device)
+    if world > 1 and not args.no_extras:
+        # alignment shards by stream with no exchange: every rank aligns the 4 096 detections
+        # of its own 16 frames (weak scaling); time = max over ranks
+        extras["align_sharded"] = align_sharded(frp, torch, dist, device, rank, world)
     # other batch sizes against the same resident gallery (config C3: batch 1 and 1024)
     if args.also_batches:
         other = {}
@@ -449,6 +453,38 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def align_sharded(frp, torch, dist, device, rank, world):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import frp_oracle_np as o
+    F, H, W_, per = 16, 1080, 1920, 256
+    rng = np.random.default_rng(50 + rank)
+    frames = torch.from_numpy(rng.integers(0, 256, (F, H, W_, 3), dtype=np.uint8)).to(device)
+    fi, lm = o.synth_detections(F, per, H, W_, seed=70 + rank)
+    d_fi, d_lm = torch.from_numpy(fi).to(device), torch.from_numpy(lm).to(device)
+    ncrop = F * per
+    blob = torch.empty((ncrop, 3, 112, 112), dtype=torch.float16, device=device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    st = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for i in range(8):
+        flush.fill_(i)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frp.align.norm_crop_batch_device(frames, F, H, W_, 3 * W_, d_fi, d_lm, ncrop, blob,
+                                         device=device.index, stream=st)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i >= 3:
+            ts.append(float(t.item()) / 1e3)
+    tm = float(np.mean(ts))
+    return {"crops_per_s": world * ncrop / tm, "call_ms_max_over_ranks": tm * 1e3, "crops_per_rank": ncrop,
+            "scaling": "weak", "workload": "per rank: 4096 detections from 16 1080p frames, no exchange"}
 
 
 def side_measurements(args, frp, torch, gal, queries, pk, device):

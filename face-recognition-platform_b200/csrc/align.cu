@@ -583,6 +583,15 @@ int frp_align_device(int device, const uint8_t* frames_dev, int F, int H, int W,
     int ndev = 0;
     int rc = frp_device_count(&ndev);
     if (rc) return rc;
+    // a buffer that lives on another GPU would fault inside the kernel: refuse it here
+    for (const void* p : {(const void*)frames_dev, (const void*)out_blob_dev}) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != device) {
+            set_error("frp_align_device: buffer lives on device %d, call names device %d", pa.device, device);
+            return FRP_E_INVALID;
+        }
+        cudaGetLastError();
+    }
     DeviceGuard dg(device);
     return align_device_impl(device, frames_dev, F, H, W, stride, frame_idx_dev, lmk_dev, M_dev, n,
                              out_blob_dev, out_aligned_dev, (cudaStream_t)stream);

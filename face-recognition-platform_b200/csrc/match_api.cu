@@ -169,6 +169,16 @@ int frp_match_device(frp_gallery_t* g, const float* queries_dev, int B, double t
                      int32_t* out_status_dev, void* stream) {
     int rc = check_match_args(g, queries_dev, B, k, out_idx_dev, out_score_dev, out_count_dev);
     if (rc) return rc;
+    // buffers of another GPU would fault inside the kernels: refuse them here
+    for (const void* p : {(const void*)queries_dev, (const void*)out_idx_dev}) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+            pa.device != g->device) {
+            set_error("frp_match_device: buffer lives on device %d, the gallery on device %d", pa.device, g->device);
+            return FRP_E_INVALID;
+        }
+        cudaGetLastError();
+    }
     std::shared_lock<std::shared_mutex> lk(g->mu);
     DeviceGuard dg(g->device);
     return match_device_locked(g, queries_dev, B, tau, k, flags, (flags & FRP_MATCH_WIDE) ? 64 : pick_kp(k),

@@ -13,11 +13,11 @@ from .gallery import Gallery, GalleryDict
 from .face_service import FaceService
 from . import align
 from .camera_scan import scan_cameras
-from .shard import ShardedMatcher, shard_bounds
+from .shard import ShardedMatcher, shard_bounds, shard_streams
 
 __all__ = [
     "FrpError", "METRIC_COS", "METRIC_L2", "MATCH_FORCE_EXACT", "MATCH_FORCE_GEMM", "MATCH_FORCE_SCAN",
     "MATCH_NO_THRESHOLD", "MATCH_STRICT", "STATUS_OK", "STATUS_FALLBACK", "STATUS_UNCERTIFIED",
     "device_count", "kernel_launches", "last_match_path", "Gallery", "GalleryDict", "FaceService",
-    "align", "ShardedMatcher", "shard_bounds", "scan_cameras",
+    "align", "ShardedMatcher", "shard_bounds", "shard_streams", "scan_cameras",
 ]

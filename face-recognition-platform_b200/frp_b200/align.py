@@ -56,9 +56,13 @@ def norm_crop_batch(frames, frame_idx, lmk=None, M=None, device: int = 0,
 
 
 def norm_crop_batch_device(frames_dev, F: int, H: int, W: int, stride: int, frame_idx_dev, lmk_dev, n: int,
-                           out_blob_dev, out_aligned_dev=None, M_dev=None, device: int = 0,
+                           out_blob_dev, out_aligned_dev=None, M_dev=None, device: Optional[int] = None,
                            stream: int = 0) -> None:
-    """Device-buffer path (torch tensors or raw pointers); asynchronous on ``stream``."""
+    """Device-buffer path (torch tensors or raw pointers); asynchronous on ``stream``.
+    ``device`` defaults to the device of ``frames_dev`` when that is a CUDA tensor, else 0."""
+    if device is None:
+        dev = getattr(frames_dev, "device", None)
+        device = dev.index if (dev is not None and getattr(dev, "index", None) is not None) else 0
     check(lib.frp_align_device(int(device), ptr(frames_dev), int(F), int(H), int(W), int(stride),
                                ptr(frame_idx_dev), ptr(lmk_dev), ptr(M_dev), int(n), ptr(out_blob_dev),
                                ptr(out_aligned_dev), stream or None))

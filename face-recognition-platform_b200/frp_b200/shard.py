@@ -50,6 +50,15 @@ def shard_bounds(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]
     return lo, hi
 
 
+def shard_streams(stream_ids, world_size: int, rank: int) -> list:
+    """Streams (cameras) whose frames ``rank`` aligns.  Alignment has no cross-frame state, so
+    the stage shards by stream with no exchange: every rank aligns the detections
+    of its own cameras and feeds the embeddings into the (row-sharded) matcher.  The assignment
+    is deterministic and balanced: ids in sorted order, dealt round-robin."""
+    ids = sorted(stream_ids, key=lambda v: (str(type(v)), v))
+    return [sid for i, sid in enumerate(ids) if i % int(world_size) == int(rank)]
+
+
 class ShardedMatcher:
     """Per-rank matcher over a row shard.
 

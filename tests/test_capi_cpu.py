@@ -11,7 +11,7 @@ import pytest
 import frp_b200
 from frp_b200 import _capi
 from frp_b200.gallery import GalleryDict
-from frp_b200.shard import record_bytes, shard_bounds, unpack_records
+from frp_b200.shard import record_bytes, shard_bounds, shard_streams, unpack_records
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -166,6 +166,16 @@ def test_shard_bounds_partition():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_streams_partition():
+    cams = ["cam%02d" % i for i in (7, 3, 11, 0, 5, 9, 1)]
+    for world in (1, 2, 4, 8):
+        parts = [shard_streams(cams, world, r) for r in range(world)]
+        assert sorted(sum(parts, [])) == sorted(cams)              # every stream exactly once
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1    # balanced
+        assert parts == [shard_streams(list(reversed(cams)), world, r) for r in range(world)]   # order-free
+    assert shard_streams([3, 1, 2], 2, 0) == [1, 3] and shard_streams([3, 1, 2], 2, 1) == [2]
 
 
 def test_record_pack_roundtrip():

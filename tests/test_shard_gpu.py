@@ -121,3 +121,28 @@ def test_single_rank_sharded_matcher_runs_end_to_end():
     torch.cuda.synchronize()
     widx, wsc, wcnt = o.cos_match_topk(G, Q, 0.3, 5, False)
     assert np.array_equal(idx.cpu().numpy(), widx) and int(anyst.item()) == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_buffers_on_another_gpu_are_refused_not_faulted():
+    """Device entry points name a device (or a gallery that lives on one); buffers of a different
+    GPU are rejected with FRP_E_INVALID instead of faulting inside a kernel."""
+    from frp_b200 import align
+    G = o.synth_cos_gallery(2000, 512, seed=5)
+    gal = Gallery(512, METRIC_COS, device=0)
+    gal.append(G)
+    q = torch.zeros((2, 512), device="cuda:1")
+    outs = (torch.empty((2, 3), dtype=torch.int64, device="cuda:1"), torch.empty((2, 3), device="cuda:1"),
+            torch.empty((2,), dtype=torch.int32, device="cuda:1"), torch.empty((2,), dtype=torch.int32, device="cuda:1"))
+    with pytest.raises(frp_b200.FrpError):
+        gal.match_device(q, 2, 0.3, 3, 0, *outs)
+    frames = torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device="cuda:1")
+    fi = torch.zeros((1,), dtype=torch.int32, device="cuda:1")
+    lm = torch.from_numpy(o.ARCFACE_DST[None].astype(np.float32)).to("cuda:1")
+    blob = torch.empty((1, 3, 112, 112), dtype=torch.float16, device="cuda:1")
+    with pytest.raises(frp_b200.FrpError):
+        align.norm_crop_batch_device(frames, 1, 64, 64, 192, fi, lm, 1, blob, device=0)
+    # the device is taken from the frames tensor when it is not named
+    align.norm_crop_batch_device(frames, 1, 64, 64, 192, fi, lm, 1, blob)
+    torch.cuda.synchronize(1)
+    assert torch.all(blob == -1.0)
