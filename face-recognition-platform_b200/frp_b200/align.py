@@ -55,6 +55,26 @@ def norm_crop_batch(frames, frame_idx, lmk=None, M=None, device: int = 0,
     return blob, aligned
 
 
+def _only_112(image_size: int, mode: str) -> None:
+    if int(image_size) != OUT or mode != "arcface":
+        raise ValueError("only insightface's arcface template at image_size=112 is built (got %r, %r)"
+                         % (image_size, mode))
+
+
+def norm_crop(img, landmark, image_size: int = OUT, mode: str = "arcface") -> np.ndarray:
+    """insightface ``face_align.norm_crop(img, landmark, image_size=112, mode='arcface')``:
+    one BGR frame + its 5x2 landmarks -> the aligned uint8 [112,112,3] crop."""
+    _only_112(image_size, mode)
+    return norm_crop_batch(np.asarray(img)[None], [0], lmk=np.asarray(landmark)[None], return_aligned=True)[1][0]
+
+
+def norm_crop2(img, landmark, image_size: int = OUT, mode: str = "arcface"):
+    """insightface ``face_align.norm_crop2``: (aligned crop, the 2x3 matrix that produced it)."""
+    _only_112(image_size, mode)
+    M = estimate_norm(np.asarray(landmark)[None])[0]
+    return norm_crop_batch(np.asarray(img)[None], [0], M=M[None], return_aligned=True)[1][0], M
+
+
 def norm_crop_batch_device(frames_dev, F: int, H: int, W: int, stride: int, frame_idx_dev, lmk_dev, n: int,
                            out_blob_dev, out_aligned_dev=None, M_dev=None, device: Optional[int] = None,
                            stream: int = 0) -> None:

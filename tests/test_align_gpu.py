@@ -79,6 +79,19 @@ def test_fully_outside_and_degenerate():
     assert align.norm_crop_batch(frames, [], lmk=np.zeros((0, 5, 2), np.float32))[0].shape == (0, 3, 112, 112)
 
 
+def test_insightface_single_image_signatures():
+    frames = o.synth_frames(1, 360, 480, seed=71)
+    fi, lm = o.synth_detections(1, 3, 360, 480, seed=72, sigma_range=(0.6, 1.5))
+    for l in lm:
+        M = o.estimate_norm(l)
+        want = oc.warp_affine(frames[0], M)
+        assert np.array_equal(align.norm_crop(frames[0], l), want)
+        got, M2 = align.norm_crop2(frames[0], l)
+        assert np.array_equal(got, want) and np.abs(M2 - M).max() < 1e-9
+    with pytest.raises(ValueError):
+        align.norm_crop(frames[0], lm[0], image_size=128)
+
+
 def test_caller_matrices_all_sign_patterns():
     """Caller-supplied 2x3 maps: every rotation quadrant, reflections, shear, scales 0.2-4 and
     translations that push part (or all, up to the int16 saturation of cv::remap) of the
