@@ -322,7 +322,9 @@ def run_ours(args):
     rows_local = hi - lo
     flops = 2.0 * B * rows_local * 512
     gbytes = rows_local * 1024 / 1e9
-    if path == "gemm_tcgen05":
+    # the tcgen05 kernel is tensor-bound from ~200 queries per pass (ridge of the measured peaks:
+    # 1 636.9 TFLOP/s / 6.56 TB/s = 250 flop/B = batch 250); below that it streams at HBM speed
+    if path == "gemm_tcgen05" and B >= 192:
         ach = flops / t_pref / 1e12
         roof = {"bound": "tensor", "kernel": "match_gemm_tcgen05", "achieved": ach, "peak": pk["tensor_burst"],
                 "unit": "TFLOP/s", "frac": ach / pk["tensor_burst"], "traffic": None,
@@ -330,17 +332,18 @@ def run_ours(args):
                 "frac_of_sustained_peak": ach / pk["tensor"], "sustained_peak": pk["tensor"],
                 "hbm_achieved_gbs": gbytes / t_pref, "hbm_frac": gbytes / t_pref / pk["hbm"]}
     else:
-        passes = (B + 3) // 4
+        passes = 1 if path == "gemm_tcgen05" else (B + 3) // 4
         ach = gbytes * passes / t_pref
-        roof = {"bound": "hbm", "kernel": "match_scan_f16", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "match_gemm_tcgen05" if path == "gemm_tcgen05" else "match_scan_f16",
+                "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"] + " copy bandwidth",
-                "note": "%d passes of 4 queries over the gallery (tcgen05 path not active)" % passes}
+                "note": "%d pass(es) over the gallery per step, path %s" % (passes, path)}
     # DRAM traffic per launch: ratio (dram bytes / algorithmic bytes) measured once with
     # `ncu --set full` on the same kernel (profiles/r1_traffic.json) x this launch's bytes
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[roof["kernel"]]
         roof["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * rows_local * 1024 * \
-            ((B + 3) // 4 if roof["bound"] == "hbm" else 1)
+            ((B + 3) // 4 if roof["kernel"] == "match_scan_f16" else 1)
         roof["traffic_source"] = tr["source"]
     except Exception:
         pass
@@ -515,7 +518,9 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     rows = gal.rows
     t = float(np.mean(mids)) / 1e3
     gb = rows * 1024 / 1e9
-    out["match_batch1"] = {"queries_per_s": n / (e0.elapsed_time(e1) / 1e3), "kernel": "match_scan_f16",
+    b1_path = frp.last_match_path()
+    out["match_batch1"] = {"queries_per_s": n / (e0.elapsed_time(e1) / 1e3),
+                           "kernel": "match_gemm_tcgen05" if b1_path == "gemm_tcgen05" else "match_scan_f16",
                            "kernel_ms": t * 1e3,
                            "roofline": {"bound": "hbm", "achieved": gb / t, "peak": pk["hbm"], "unit": "GB/s",
                                         "frac": gb / t / pk["hbm"]}}

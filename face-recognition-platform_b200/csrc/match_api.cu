@@ -62,8 +62,14 @@ int match_device_locked(frp_gallery* g, const float* q_dev, int B, double tau, i
     const bool exact = (flags & FRP_MATCH_FORCE_EXACT) != 0;
     bool use_gemm = false;
     if (!exact && KP <= 32 && gemm_supported(g)) {
+        // B > 4: tensor cores.  B <= 4 is HBM-bound on either kernel; on large galleries the
+        // tcgen05 kernel's 2-D TMA ring streams faster than the scan kernel's FMA loop keeps up
+        // with (4 M x 512: 0.566 vs 0.60-0.63 ms; 4 M x 128, B = 4: 0.158 vs 0.243 ms), on small
+        // ones the scan kernel has the shorter ramp (200 k x 128: 14 vs 30 us)
+        const size_t gbytes = (size_t)g->rows * g->dimp * sizeof(__half);
+        const bool big = gbytes >= ((size_t)256 << 20) && (g->dimp >= 256 || B >= 3);
         if (flags & FRP_MATCH_FORCE_GEMM) use_gemm = true;
-        else if (!(flags & FRP_MATCH_FORCE_SCAN) && B > 4) use_gemm = true;
+        else if (!(flags & FRP_MATCH_FORCE_SCAN) && (B > 4 || big)) use_gemm = true;
     }
     if ((flags & FRP_MATCH_FORCE_GEMM) && !use_gemm) {
         set_error("frp_match: tcgen05 path not available for this gallery (dimp=%d)", g->dimp);

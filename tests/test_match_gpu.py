@@ -582,9 +582,13 @@ def test_full_size_10m_properties():
     for j in range(B):
         assert np.array_equal(i2[j, :cnt[j]], idx[j, :cnt[j]])
     for j in (0, 1, 101, 254):
-        i1, s1, c1, _ = full.match(Q[j:j + 1], tau, k, MATCH_NO_THRESHOLD)
+        i1, s1, c1, _ = full.match(Q[j:j + 1], tau, k, MATCH_NO_THRESHOLD | MATCH_FORCE_SCAN)
         assert frp_b200.last_match_path() == "scan_f16"
         assert np.array_equal(i1[0], i2[j]) and np.array_equal(s1[0], s2[j])
+        # a gallery this large routes single queries through the tcgen05 kernel by default
+        i0, s0, c0, _ = full.match(Q[j:j + 1], tau, k, MATCH_NO_THRESHOLD)
+        assert frp_b200.last_match_path() == "gemm_tcgen05"
+        assert np.array_equal(i0[0], i2[j]) and np.array_equal(s0[0], s2[j])
     # shard invariance at full size: two 5M shards merged == one 10M gallery
     parts = [h.match(Q, tau, k, MATCH_NO_THRESHOLD) for h in halves]
     for j in range(B):

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--tau", type=float, default=None)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--flags", type=lambda v: int(v, 0), default=0, help="FRP_MATCH_* flags, e.g. 0x4 = force tcgen05")
     a = ap.parse_args()
     metric = frp.METRIC_L2 if a.metric == "l2" else frp.METRIC_COS
     tau = a.tau if a.tau is not None else (0.6 if a.metric == "l2" else 0.4)
@@ -47,7 +48,7 @@ def main():
     from frp_b200 import _capi
     _capi.lib.frp_profile_enable(1)
     for _ in range(a.iters):
-        gal.match_device(q.data_ptr(), a.batch, tau, a.k, 0, idx.data_ptr(), sc.data_ptr(), cnt.data_ptr(),
+        gal.match_device(q.data_ptr(), a.batch, tau, a.k, a.flags, idx.data_ptr(), sc.data_ptr(), cnt.data_ptr(),
                          st.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
     t = [C.c_float(), C.c_float(), C.c_float()]
