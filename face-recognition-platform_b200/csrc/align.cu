@@ -38,7 +38,10 @@ namespace {
 constexpr int kOut = 112;
 constexpr int kTileW = 16;
 constexpr int kTilesX = kOut / kTileW;              // 7
-constexpr int kWarps = 18;                          // what fits in 227 KB of shared memory
+#ifndef FRP_ALIGN_WARPS
+#define FRP_ALIGN_WARPS 18
+#endif
+constexpr int kWarps = FRP_ALIGN_WARPS;             // what fits in 227 KB of shared memory
 #ifndef FRP_ALIGN_ITEMS
 #define FRP_ALIGN_ITEMS 7     // measured (C4): 2 -> 0.183 ms, 4 -> 0.170 ms, 7 -> 0.165 ms
 #endif
@@ -52,10 +55,13 @@ __constant__ int c_box_h[kNumH] = {8, 14, 22, 34, 46};       // rows
 constexpr int kHostBoxW[kNumW] = {64, 96, 128, 176, 224};
 constexpr int kHostBoxH[kNumH] = {8, 14, 22, 34, 46};
 constexpr int kMaxBoxW = 224, kMaxBoxH = 46;
-constexpr int kBufBytes = 10368;                    // >= 224*46 + 16 slack, multiple of 128
+#ifndef FRP_ALIGN_BUF
+#define FRP_ALIGN_BUF 10368
+#endif
+constexpr int kBufBytes = FRP_ALIGN_BUF;            // >= 224*46 + 16 slack, multiple of 128
 constexpr int kTabBytes = 4 * kOut * 4;             // adelta, bdelta, X0, Y0 (1792 = 14*128)
-constexpr int kHalfBuf = 5120;                      // boxes up to this size are double buffered inside kBufBytes
-constexpr int kWarpSmem = 12288;                    // tab + buffer + mbarriers, multiple of 128
+constexpr int kHalfBuf = (kBufBytes / 2) & ~127;     // boxes up to this size are double buffered inside kBufBytes
+constexpr int kWarpSmem = kTabBytes + kBufBytes + 128;   // tab + buffer + mbarriers, multiple of 128
 
 struct TmapSet {
     CUtensorMap m[kNumW * kNumH];
@@ -174,7 +180,7 @@ __device__ __forceinline__ bool plan_box(double ax, double ay, double bx, double
     for (int i = 0; i < kNumW - 1; ++i) wi += (need_w > c_box_w[i]) ? 1 : 0;
 #pragma unroll
     for (int i = 0; i < kNumH - 1; ++i) hi += (need_h > c_box_h[i]) ? 1 : 0;
-    return true;
+    return c_box_w[wi] * c_box_h[hi] <= kBufBytes;
 }
 
 // locate the box of output tile (x0,y0) and start its TMA load into buf
