@@ -126,6 +126,45 @@ def test_caller_matrices_all_sign_patterns():
     assert sum(int(a.any()) for a in al) > 100      # most crops do show the frame
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_frames_strides_and_maps(seed):
+    """Random frame sizes (pitches that are and are not 16-byte multiples, frames smaller than a
+    TMA box, single-row-ish frames), random similarity / affine maps and landmark-driven crops."""
+    rng = np.random.default_rng(900 + seed)
+    for _ in range(5):
+        H, W = int(rng.integers(8, 420)), int(rng.integers(8, 520))
+        F = int(rng.integers(1, 4))
+        frames = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+        n = 10
+        fi = rng.integers(0, F, n).astype(np.int32)
+        Ms = []
+        for i in range(n):
+            th = rng.uniform(0, 2 * np.pi)
+            sc = float(np.exp(rng.uniform(np.log(0.15), np.log(6.0))))
+            A = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]) * sc
+            if i % 3 == 0:
+                A = A @ np.array([[1.0, rng.uniform(-0.5, 0.5)], [rng.uniform(-0.3, 0.3), rng.choice([-1.0, 1.0])]])
+            c = np.array([rng.uniform(-0.2 * W, 1.2 * W), rng.uniform(-0.2 * H, 1.2 * H)])
+            Ms.append(np.hstack([A, (np.array([56.0, 56.0]) - A @ c)[:, None]]))
+        M = np.stack(Ms)
+        blob, al = align.norm_crop_batch(frames, fi, M=M, return_aligned=True)
+        wal, wbl = _oracle_batch(frames, fi, M)
+        assert np.array_equal(al, wal), (seed, H, W)
+        assert np.array_equal(blob, wbl), (seed, H, W)
+        # landmark-driven crops on the same frames
+        lm = np.empty((6, 5, 2), np.float32)
+        for i in range(6):
+            th, sg = rng.uniform(-0.6, 0.6), rng.uniform(0.2, 2.5)
+            R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            ctr = np.array([rng.uniform(-0.1 * W, 1.1 * W), rng.uniform(-0.1 * H, 1.1 * H)])
+            lm[i] = ((o.ARCFACE_DST.astype(np.float64) - 56.0) @ R.T) * sg + ctr + rng.normal(0, 0.7, (5, 2))
+        fi2 = rng.integers(0, F, len(lm)).astype(np.int32)
+        blob2, al2 = align.norm_crop_batch(frames, fi2, lmk=lm, return_aligned=True)
+        M2 = np.stack([o.estimate_norm(l) for l in lm])
+        wal2, wbl2 = _oracle_batch(frames, fi2, M2)
+        assert np.array_equal(al2, wal2) and np.array_equal(blob2, wbl2), (seed, H, W)
+
+
 def test_device_path_many_crops():
     """BASELINE.json configs[3] at full size: 4 096 detections from 16 1080p frames."""
     import torch
