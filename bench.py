@@ -236,7 +236,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # stdout carries exactly one JSON line: while the communicator comes up (NCCL prints its
+        # version banner there when NCCL_DEBUG is set, as it is in this image) fd 1 points at stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     pk = peaks()
     B, k, tau, K, W = args.batch, args.k, args.tau, args.steps, args.warmup
 
