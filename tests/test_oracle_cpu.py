@@ -139,3 +139,42 @@ def test_live_reference_agrees_with_np_oracle():
         assert fs.batch_compare_faces(list(Q)) == o.batch_compare_faces(ENC, list(Q), 0.6)
     finally:
         ENC.clear()
+
+
+def test_umeyama_cross_checked_against_scipy_and_opencv():
+    """scikit-image (whose ``_umeyama`` insightface calls) is not in this image, so the
+    restatement cannot be pinned to it; it is cross-checked against two independent
+    implementations of the same least-squares similarity instead: SciPy's orthogonal
+    Procrustes solution and OpenCV's ``estimateAffinePartial2D`` (all five points inliers,
+    LM-refined), plus the first-order optimality of the residual."""
+    cv2 = pytest.importorskip("cv2")
+    from scipy.linalg import orthogonal_procrustes
+    rng = np.random.default_rng(77)
+    dst = o.ARCFACE_DST.astype(np.float64)
+    for _ in range(40):
+        th, sg = rng.uniform(-0.9, 0.9), rng.uniform(0.3, 4.0)
+        R0 = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        src = ((dst - 56.0) @ R0.T) * sg + rng.uniform(100, 900, 2) + rng.normal(0, 1.5, (5, 2))
+        src32 = src.astype(np.float32)
+        M = o.estimate_norm(src32)                       # 2x3, maps src -> dst
+        s = src32.astype(np.float64)
+        sc, dc = s - s.mean(0), dst - dst.mean(0)
+        Rp, _ = orthogonal_procrustes(sc, dc)            # min ||sc Rp - dc||_F, Rp orthogonal
+        assert np.linalg.det(Rp) > 0
+        scale = np.trace(Rp.T @ sc.T @ dc) / np.sum(sc * sc)
+        A = scale * Rp.T
+        Mp = np.hstack([A, (dst.mean(0) - A @ s.mean(0))[:, None]])
+        assert np.abs(M - Mp).max() < 1e-9
+        Mc, inl = cv2.estimateAffinePartial2D(s, dst, method=cv2.LMEDS, refineIters=50)
+        if inl is not None and int(inl.sum()) == 5:
+            assert np.abs(M - Mc).max() < 5e-3 * max(1.0, np.abs(M).max())
+        # least-squares optimum: no first-order decrease along any of the 4 similarity parameters
+        def resid(Mx):
+            return float(np.sum((s @ Mx[:, :2].T + Mx[:, 2] - dst) ** 2))
+        r0 = resid(M)
+        a, b, tx, ty = M[0, 0], M[1, 0], M[0, 2], M[1, 2]
+        for da, db, dx, dy in [(1e-5, 0, 0, 0), (0, 1e-5, 0, 0), (0, 0, 1e-3, 0), (0, 0, 0, 1e-3)]:
+            for sgn in (1, -1):
+                a2, b2 = a + sgn * da, b + sgn * db
+                M2 = np.array([[a2, -b2, tx + sgn * dx], [b2, a2, ty + sgn * dy]])
+                assert resid(M2) >= r0 - 1e-9
