@@ -152,7 +152,7 @@ class ShardedMatcher:
         if self.world > 1:
             dist.all_gather_into_tensor(recv, send, group=self.group)
         else:
-            recv.copy_(send)
+            recv = send               # a single shard: merge straight from the local record
         self._merge(m, self.world, B, k, recv, out_idx, out_score, out_count, any_status, stream)
         return out_idx, out_score, out_count, any_status
 
