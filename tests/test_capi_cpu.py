@@ -189,3 +189,19 @@ def test_record_pack_roundtrip():
         rec[B * k * 12:B * k * 12 + B * 4].view(np.int32)[:] = r + 1
     idx, sc, cnt, st = unpack_records(buf, R, B, k)
     assert idx.shape == (R, B, k) and idx[1, 0, 0] == 100 and sc[1, 0, 1] == 1.5 and cnt[1, 2] == 2
+
+
+def test_built_library_contains_the_blackwell_instructions():
+    """The shipped .so is sm_100a code with the instructions the design names (no library or
+    generic fallback): tcgen05 MMAs incl. the cta_group::2 form, TMEM loads, tiled and bulk TMA,
+    multicast commits, and the integer dot product of the alignment blend."""
+    import shutil
+    import subprocess
+    from frp_b200 import _capi
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _capi._LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for op in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG.2D", "UTMALDG.2D.2CTA", "UTMALDG.2D.MULTICAST",
+               "UTMALDG.3D", "UBLKCP", "UTCBAR.2CTA.MULTICAST", "IDP.2A"):
+        assert op in sass, op
