@@ -712,8 +712,7 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
                         (l2 ? kNormRingBytes : 0);
     const int lpc = gemm_lpc(g);
     dim3 grid(nlists / lpc, groups);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads_for(lpc));
     cfg.dynamicSmemBytes = smem;
