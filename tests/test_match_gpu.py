@@ -340,6 +340,25 @@ def test_tcgen05_pair_kernel_dims_metrics(B, dim, metric):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("N", [1, 100, 257, 700])
+def test_tcgen05_pair_kernel_tiny_galleries(N):
+    """Fewer gallery tiles than CTA pairs: one (partial) tile per pair, the rest of the grid is
+    capped away; batches of 256 and 512 queries."""
+    rng = np.random.default_rng(N)
+    G = rng.standard_normal((N, 512)).astype(np.float32)
+    gal = Gallery(512, METRIC_COS)
+    gal.append(G)
+    for B in (256, 512):
+        Q = rng.standard_normal((B, 512)).astype(np.float32)
+        Q[::3] = G[rng.integers(0, N, len(Q[::3]))] + 0.05 * Q[::3]
+        a = gal.match(Q, 0.3, 5, MATCH_FORCE_GEMM)
+        assert frp_b200.last_match_path() == "gemm_tcgen05" and np.all(a[3] == 0)
+        b = gal.match(Q, 0.3, 5, MATCH_FORCE_EXACT)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2])
+        widx, wsc, wcnt = o.cos_match_topk(G, Q[:16], 0.3, 5, True)
+        assert exact_equal(a[0][:16], a[2][:16], widx, wcnt)
+
+
 @pytest.mark.parametrize("dim", [64, 100, 128, 256, 384, 512])
 @pytest.mark.parametrize("metric", [METRIC_L2, METRIC_COS])
 def test_dims_and_metrics(dim, metric):
