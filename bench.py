@@ -49,9 +49,13 @@ def parse():
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
-        d = json.load(open(p))
-        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"],
-                "src": "measured"}
+        try:
+            d = json.load(open(p))
+            burst = float(d["bf16_tflops"])
+            return {"hbm": float(d["hbm_gbs"]), "tensor_burst": burst,
+                    "tensor": float(d.get("bf16_tflops_sustained", burst)), "src": "measured"}
+        except Exception:      # unreadable or incomplete file: documented fallback below
+            pass
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
 
 
