@@ -150,3 +150,46 @@ def test_empty_gallery_and_bad_input_follow_the_never_raise_convention(pair):
     _same(ref.store_face("a", np.ones(128) * 0.01), ours.store_face("a", np.ones(128) * 0.01))
     # wrong query length: the reference logs and returns [], so does the mirror
     assert ref.compare_faces(np.zeros(64)) == ours.compare_faces(np.zeros(64)) == []
+
+
+def test_batched_camera_scan_equals_the_reference_per_face_loop(pair):
+    """scan_cameras (one batched match for all faces of all cameras) against the loop of
+    backend/app/routes/camera.py:243-259 driven by the live reference service: every gallery row
+    with ``match and distance <= confidence_threshold``, faces in detection order, matches by
+    ascending distance; ``max_faces`` truncation as in :233-235."""
+    from frp_b200 import scan_cameras
+    ref, ours, ENC = pair
+    rng = np.random.default_rng(7)
+    people = rng.normal(0, 0.05, (60, 128)).astype(np.float32).astype(np.float64)
+    for i, g in enumerate(people):
+        ref.store_face("w%02d" % i, g)
+        ours.store_face("w%02d" % i, g)
+    # a second enrolment of some people, so one face can match several rows
+    for i in (4, 9):
+        twin = (people[i] + rng.normal(0, 0.01, 128)).astype(np.float32).astype(np.float64)
+        ref.store_face("w%02d_b" % i, twin)
+        ours.store_face("w%02d_b" % i, twin)
+
+    def face(j=None):
+        base = people[j] if j is not None else rng.normal(0, 0.05, 128)
+        return (base + rng.normal(0, 0.02, 128)).astype(np.float32).astype(np.float64)
+
+    cams = {"gate": [face(4), face(), face(9)], "lobby": [], 7: [face(30)] + [face() for _ in range(4)],
+            "dock": [face(i) for i in (1, 2, 3, 4)]}
+    cfgs = {"gate": {"confidence_threshold": 0.6}, 7: {"confidence_threshold": 0.35, "max_faces": 3},
+            "dock": {"max_faces": 2}}
+    got = scan_cameras(ours, cams, cfgs)
+    want = {}
+    for cam, faces in cams.items():
+        cfg = cfgs.get(cam, {})
+        thr, mf = cfg.get("confidence_threshold", 0.6), cfg.get("max_faces", 10)
+        out = []
+        for enc in list(faces)[:mf]:
+            for m in ref.compare_faces(enc, target_names=None, return_distances=True):
+                if m.get("match") and m.get("distance", 0.0) <= thr:
+                    out.append({"camera_id": cam, "target": m["target"], "distance": m["distance"],
+                                "confidence": m["confidence"]})
+        want[cam] = out
+    assert list(got.keys()) == list(want.keys())
+    _same(want, got)
+    assert sum(len(v) for v in got.values()) >= 6
