@@ -68,6 +68,52 @@ def config(args, n_gpus):
 
 
 # --------------------------------------------------------------------------
+# Synthetic workloads.  bench.py generates its own inputs; `oracle/` is imported
+# only by the cpu_baseline legs below (and by `--impl reference`).
+# --------------------------------------------------------------------------
+_ARCFACE_DST = np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366],
+                         [41.5493, 92.3655], [70.7299, 92.2041]], dtype=np.float32)
+
+
+def synth_detections(nframes, per_frame, H=1080, W=1920, seed=7, sigma_range=(0.4, 3.0), oob_frac=0.02):
+    """Landmarks = ((arcface_dst - 56) @ R(theta)^T) * sigma + centre + N(0, 1 px): magnification
+    sigma source px per template px, roll theta in [-0.5, 0.5] rad, a few detections at the frame
+    border."""
+    rng = np.random.default_rng(seed)
+    n = nframes * per_frame
+    frame_idx = np.repeat(np.arange(nframes, dtype=np.int32), per_frame)
+    sigma = rng.uniform(*sigma_range, n)
+    theta = rng.uniform(-0.5, 0.5, n)
+    cx = rng.uniform(150, W - 150, n)
+    cy = rng.uniform(150, H - 150, n)
+    oob = rng.random(n) < oob_frac
+    cx[oob] = rng.choice([10.0, W - 10.0], int(oob.sum()))
+    cy[oob] = rng.choice([10.0, H - 10.0], int(oob.sum()))
+    base = _ARCFACE_DST.astype(np.float64) - 56.0
+    lm = np.empty((n, 5, 2), np.float32)
+    for i in range(n):
+        c, s = np.cos(theta[i]), np.sin(theta[i])
+        R = np.array([[c, -s], [s, c]])
+        lm[i] = ((base @ R.T) * sigma[i] + np.array([cx[i], cy[i]]) + rng.normal(0, 1.0, (5, 2))).astype(np.float32)
+    return frame_idx, lm
+
+
+def synth_l2_gallery(n=1000, dim=128, seed=1234):
+    """128-d encodings ~ N(0, 0.05): impostor distance ~0.8, no impostor match at tolerance 0.6."""
+    return np.random.default_rng(seed).normal(0, 0.05, (n, dim))
+
+
+def synth_l2_queries(G, nq, seed=4321, planted_frac=0.5):
+    rng = np.random.default_rng(seed)
+    n, dim = G.shape
+    Q = rng.normal(0, 0.05, (nq, dim))
+    planted = rng.random(nq) < planted_frac
+    j = rng.integers(0, n, nq)
+    Q[planted] = G[j[planted]] + rng.normal(0, 0.02, (int(planted.sum()), dim))
+    return Q, np.where(planted, j, -1)
+
+
+# --------------------------------------------------------------------------
 # CPU baseline: the reference's numpy path (oracle port) on the host cores
 # --------------------------------------------------------------------------
 def cpu_match_sample(args, rows_sample=500_000, reps=3):
@@ -475,12 +521,10 @@ def run_ours(args):
 
 
 def align_sharded(frp, torch, dist, device, rank, world):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import frp_oracle_np as o
     F, H, W_, per = 16, 1080, 1920, 256
     rng = np.random.default_rng(50 + rank)
     frames = torch.from_numpy(rng.integers(0, 256, (F, H, W_, 3), dtype=np.uint8)).to(device)
-    fi, lm = o.synth_detections(F, per, H, W_, seed=70 + rank)
+    fi, lm = synth_detections(F, per, H, W_, seed=70 + rank)
     d_fi, d_lm = torch.from_numpy(fi).to(device), torch.from_numpy(lm).to(device)
     ncrop = F * per
     blob = torch.empty((ncrop, 3, 112, 112), dtype=torch.float16, device=device)
@@ -542,11 +586,11 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
                                         "frac": gb / t / pk["hbm"]}}
     # alignment: 4096 detections from 16 1080p frames -> 112x112 fp16 NCHW
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import frp_oracle_np as o
+    import frp_oracle_np as o      # cpu_baseline legs only (align and C1 below)
     F, H, W_, per = 16, 1080, 1920, 256
     rng = np.random.default_rng(5)
     frames = torch.from_numpy(rng.integers(0, 256, (F, H, W_, 3), dtype=np.uint8)).to(device)
-    fi, lm = o.synth_detections(F, per, H, W_, seed=7)
+    fi, lm = synth_detections(F, per, H, W_, seed=7)
     d_fi = torch.from_numpy(fi).to(device)
     d_lm = torch.from_numpy(lm).to(device)
     ncrop = F * per
@@ -626,8 +670,8 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     # config C1: face_recognition compare_faces, 1 query vs 1k synthetic 128-d encodings,
     # tolerance 0.6, through the drop-in FaceService (all 1 000 result dicts, like the reference)
     try:
-        G1 = o.synth_l2_gallery(1000, 128, seed=1234)
-        Q1, _ = o.synth_l2_queries(G1, 64, seed=4321)
+        G1 = synth_l2_gallery(1000, 128, seed=1234)
+        Q1, _ = synth_l2_queries(G1, 64, seed=4321)
         enc = frp.GalleryDict()
         enc.bulk_load(["id%07d" % i for i in range(len(G1))], G1)
         fs = frp.FaceService(enc, tolerance=0.6, raise_errors=True)
@@ -661,7 +705,7 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     try:
         S_, faces = 32, 8
         fr32 = torch.from_numpy(rng.integers(0, 256, (S_, H, W_, 3), dtype=np.uint8)).to(device)
-        fi5, lm5 = o.synth_detections(S_, faces, H, W_, seed=11)
+        fi5, lm5 = synth_detections(S_, faces, H, W_, seed=11)
         d_fi5, d_lm5 = torch.from_numpy(fi5).to(device), torch.from_numpy(lm5).to(device)
         n5 = S_ * faces
         blob5 = torch.empty((n5, 3, 112, 112), dtype=torch.float16, device=device)

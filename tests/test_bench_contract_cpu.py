@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -34,3 +36,22 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_generates_the_surveyed_workloads_itself():
+    """bench.py builds its own synthetic inputs (oracle/ is reserved for the checker and the
+    cpu_baseline legs); they are the SURVEY 8d workloads, identical to the oracle's generators."""
+    import importlib.util
+    import frp_oracle_np as o
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a, b = bench.synth_detections(4, 32, 1080, 1920, seed=7), o.synth_detections(4, 32, 1080, 1920, seed=7)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    G = bench.synth_l2_gallery(1000, 128, seed=1234)
+    assert np.array_equal(G, o.synth_l2_gallery(1000, 128, seed=1234))
+    q1, q2 = bench.synth_l2_queries(G, 64, seed=4321), o.synth_l2_queries(G, 64, seed=4321)
+    assert np.array_equal(q1[0], q2[0]) and np.array_equal(q1[1], q2[1])
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    body = src.split("def align_sharded", 1)[1].split("\ndef ", 1)[0]
+    assert "oracle" not in body
