@@ -94,3 +94,48 @@ def test_sharded_match_world2_gloo():
         p.join(30)
     for rank, ok, msg in res:
         assert ok, "rank %d failed: %s" % (rank, msg)
+
+
+def test_match_certified_walks_the_fallback_ladder():
+    """Host logic of ShardedMatcher.match_certified on CPU tensors (single rank, injected
+    stand-ins): an uncertified step is repeated with FRP_MATCH_FORCE_EXACT, then with
+    FORCE_EXACT | WIDE, forced-kernel flags are dropped on the way, and the level is reported."""
+    for p in (os.path.join(ROOT, "face-recognition-platform_b200"),):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    from frp_b200._capi import MATCH_FORCE_EXACT, MATCH_FORCE_GEMM, MATCH_NO_THRESHOLD, MATCH_WIDE
+    from frp_b200.shard import ShardedMatcher, unpack_records
+
+    def run(certify_at):
+        seen = []
+
+        def local_match(q_dev, B, tau, k, flags, idx, score, count, status, stream):
+            seen.append(flags)
+            idx.fill_(3)
+            score.fill_(0.5)
+            count.fill_(1)
+            level = 2 if (flags & MATCH_WIDE) else (1 if (flags & MATCH_FORCE_EXACT) else 0)
+            status.fill_(0 if level >= certify_at else 1)
+
+        def merge(metric, R, B, k, records, out_idx, out_score, out_count, any_status, stream):
+            idx, sc, cnt, st = unpack_records(records.numpy(), R, B, k)
+            out_idx.copy_(torch.from_numpy(idx[0]))
+            out_score.copy_(torch.from_numpy(sc[0]))
+            out_count.copy_(torch.from_numpy(cnt[0]))
+            any_status.fill_(int(st.max()))
+
+        m = ShardedMatcher(None, 100, 0, 1, local_match=local_match, merge=merge)
+        q = torch.zeros((4, 8))
+        oi, os_, oc, level = m.match_certified(q, 0.3, 2, flags=MATCH_FORCE_GEMM | MATCH_NO_THRESHOLD, metric=1)
+        assert oi.shape == (4, 2) and int(oc[0]) == 1
+        return level, seen
+
+    level, seen = run(0)
+    assert level == 0 and seen == [MATCH_FORCE_GEMM | MATCH_NO_THRESHOLD]
+    level, seen = run(1)
+    assert level == 1 and seen[1] == MATCH_NO_THRESHOLD | MATCH_FORCE_EXACT
+    level, seen = run(2)
+    assert level == 2 and seen[2] == MATCH_NO_THRESHOLD | MATCH_FORCE_EXACT | MATCH_WIDE and len(seen) == 3
+    level, seen = run(3)
+    assert level == 3 and len(seen) == 3
