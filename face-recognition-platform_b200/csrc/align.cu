@@ -538,10 +538,10 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     memset(&maps, 0, sizeof(maps));
     a.use_tma = encode_frame_maps(&maps, frames, F, H, W, stride, a.frame_bytes) ? 1 : 0;
     const size_t smem = (size_t)kWarps * kWarpSmem + 128;
-    static thread_local bool configured = false;
-    if (!configured) {
-        FRP_CUDA(cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    {
+        int rc = FRP_OK;
+        configure_func_smem((const void*)align_kernel, device, smem, &rc);
+        if (rc) return rc;
     }
     const int items = n * kItemsPerCrop;
     int grid = (items + kWarps - 1) / kWarps;

@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <shared_mutex>
+#include <vector>
 
 #include "frp_b200.h"
 
@@ -26,10 +27,26 @@ struct frp_gallery {
     float* g32 = nullptr;    // [capacity][dimp] fp32 master (COS: normalised)
     float* norm2 = nullptr;  // [capacity] |g|^2 of the master row
     uint8_t* alive = nullptr;  // [capacity] 1 = live, 0 = tombstone
+    // optional [capacity] global insertion sequence of each row (mutable row-sharded galleries:
+    // appends go to the least-full shard, so global order != base_row + local row); when set,
+    // results carry seq[row] and the cross-shard merge breaks ties by it
+    uint64_t* seq = nullptr;
     float* d_gmax = nullptr;   // device [2]: max |g| seen, max |g - fp16(g)| seen (monotone upper bounds)
     float gmax = 0.f;          // host copies
     float gerr = 0.f;
     int sm_count = FRP_NUM_SM_DEFAULT;
+    // host mirror of `alive` (mutations check it instead of a blocking device read)
+    std::vector<uint8_t> h_alive;
+    // row mutations: private stream + pinned staging row, so an update is one small H2D + one
+    // kernel + an 8-byte read-back on that stream (no cudaMalloc, no device-wide sync)
+    cudaStream_t mut_stream = nullptr;
+    float* h_stage = nullptr;     // pinned [dim] + 2 floats (gmax read-back)
+    float* d_stage = nullptr;     // device [dim]
+    // TMA descriptors of the fp16 scan copy ([capacity][dimp], boxes of 256 and 128 rows x 64
+    // halfs), encoded when the buffers are (re)allocated, i.e. under the unique lock
+    alignas(64) unsigned char tmap_g[128];
+    alignas(64) unsigned char tmap_gh[128];
+    bool tmap_valid = false;
     mutable std::shared_mutex mu;  // match = shared, mutate = unique
 };
 
@@ -93,8 +110,11 @@ __host__ __device__ inline uint32_t key_row(uint64_t k) { return ~(uint32_t)(k &
 
 // ---- kernels / launchers (defined in the .cu files) --------------------------
 // prep: normalise (COS), pad to dimp, make fp16 copy, fill QParams
-int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
-                        int eps_mode, float* qprep, __half* q16, QParams* qp, cudaStream_t st);
+// q_dev rows are `qstride` floats apart (dim for caller queries, dimp for gallery master rows);
+// q_rows (optional, device) gathers the queries from q_dev by row index (self-match)
+int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride, const uint64_t* q_rows,
+                        int B, double tau, int flags, int eps_mode, float* qprep, __half* q16,
+                        QParams* qp, cudaStream_t st);
 
 // streaming scan prefilter: writes cand[B][nlists][KP] keys. use_master: scan fp32 master.
 int scan_num_lists(const frp_gallery* g, bool use_master);
@@ -104,18 +124,51 @@ int launch_match_scan(const frp_gallery* g, bool use_master, const float* qprep,
 // tcgen05 prefilter (B > 4): same candidate-list contract.
 bool gemm_supported(const frp_gallery* g);
 int gemm_num_lists(const frp_gallery* g, int B);
-int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP,
+// tmap_q: the caller's cached descriptor of q16 ([groups*128][dimp] fp16), see Workspace
+int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int B, int KP,
                       uint64_t* cand, int nlists, cudaStream_t st);
+int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp);
+
+// (re)encode the gallery's cached tensor maps; caller holds the unique lock (or owns g exclusively)
+void gemm_refresh_maps(frp_gallery* g);
 
 // cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (no libcuda link); null if unavailable
 void* tensormap_encode_fn();
 
 // exact fp64 re-rank of the survivors + certificate + output
+// out_score (f32) and out_score64 (f64) are both optional; at least one is written
 int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, int B, int k, int KP,
                   int flags, double tau, const uint64_t* cand, int nlists, int64_t* out_idx,
-                  float* out_score, int32_t* out_count, int32_t* out_status, cudaStream_t st);
+                  float* out_score, double* out_score64, int32_t* out_count, int32_t* out_status,
+                  cudaStream_t st);
 
-int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, cudaStream_t st);
+int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, uint64_t out_stride,
+                  cudaStream_t st);
+
+// Per-(thread, stream) scratch of the match pipeline: grows on demand, never shrinks, so the
+// steady state issues no allocation.  Work on one stream is ordered, hence reuse is safe; a
+// thread that drives several streams gets one workspace per stream.
+struct Workspace {
+    int device = -1;
+    uint8_t* dev = nullptr;       // device scratch
+    size_t dev_bytes = 0;
+    uint8_t* pinned = nullptr;    // pinned host staging (host API only)
+    size_t pinned_bytes = 0;
+    // cached query tensor map (valid for q16_ptr / groups / dimp)
+    alignas(64) unsigned char tmap_q[128];
+    const void* q16_ptr = nullptr;
+    int q_groups = 0, q_dimp = 0;
+};
+Workspace* workspace_for(int device, cudaStream_t st);
+int workspace_reserve(Workspace* w, size_t dev_bytes, size_t pinned_bytes);
+
+// caller holds (at least) the shared lock and has set the device.  q_rows: see launch_prep_queries.
+int match_device_locked(frp_gallery* g, const float* q_dev, size_t qstride, const uint64_t* q_rows, int B,
+                        double tau, int k, int flags, int KP, int64_t* out_idx, float* out_score,
+                        double* out_score64, int32_t* out_count, int32_t* out_status, cudaStream_t st);
+int pick_kp(int k);
+cudaStream_t thread_stream(int device);
+void configure_func_smem(const void* func, int device, size_t bytes, int* rc);
 
 }  // namespace frp
 

@@ -11,8 +11,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "frp_device.cuh"
@@ -34,15 +36,37 @@ void set_error(const char* fmt, ...) {
 }
 void set_match_path(const char* name) { t_match_path = name; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: the
+// opt-in is remembered per (kernel, device), not per thread.
+void configure_func_smem(const void* func, int device, size_t bytes, int* rc) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = done[std::make_pair(func, device)];
+    if (cur >= bytes) return;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(%zu bytes of dynamic shared memory) failed: %s", bytes,
+                  cudaGetErrorString(e));
+        cudaGetLastError();
+        if (rc) *rc = FRP_E_CUDA;
+        return;
+    }
+    cur = bytes;
+}
+
 // One warp per row: fp64 norm, optional normalisation, fp32 master + fp16 copy.
+// src rows are `src_stride` floats apart; normalise = 0 ingests COS rows verbatim (snapshot load:
+// the stored master is already normalised and must stay bit-identical).
 __global__ void ingest_rows_kernel(const float* __restrict__ src, uint64_t n, int dim, int dimp,
-                                   int metric, uint64_t first_row, __half* __restrict__ g16,
+                                   uint64_t src_stride, int normalise, uint64_t first_row,
+                                   __half* __restrict__ g16,
                                    float* __restrict__ g32, float* __restrict__ norm2,
                                    uint8_t* __restrict__ alive, float* __restrict__ gmax) {
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= n) return;
-    const float* s = src + w * (uint64_t)dim;
+    const float* s = src + w * src_stride;
     double acc = 0.0;
     for (int i = lane; i < dim; i += 32) {
         const double x = (double)s[i];
@@ -50,7 +74,7 @@ __global__ void ingest_rows_kernel(const float* __restrict__ src, uint64_t n, in
     }
     acc = warp_sum_f64(acc);
     double scale = 1.0;
-    if (metric == FRP_METRIC_COS) scale = acc > 0.0 ? 1.0 / sqrt(acc) : 0.0;
+    if (normalise) scale = acc > 0.0 ? 1.0 / sqrt(acc) : 0.0;
     const uint64_t row = first_row + w;
     double acc2 = 0.0, err2 = 0.0;
     for (int i = lane; i < dimp; i += 32) {
@@ -83,7 +107,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ src32, const __half
                                    const float* __restrict__ srcn, const uint64_t* __restrict__ idx,
                                    uint64_t n, int dimp, float* __restrict__ dst32,
                                    __half* __restrict__ dst16, float* __restrict__ dstn,
-                                   uint8_t* __restrict__ dalive) {
+                                   uint8_t* __restrict__ dalive, const uint64_t* __restrict__ srcseq,
+                                   uint64_t* __restrict__ dstseq) {
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= n) return;
@@ -95,6 +120,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src32, const __half
     if (lane == 0) {
         dstn[w] = srcn[r];
         dalive[w] = 1;
+        if (srcseq) dstseq[w] = srcseq[r];
     }
 }
 
@@ -109,7 +135,9 @@ static void free_buffers(frp_gallery* g) {
     if (g->g32) cudaFree(g->g32);
     if (g->norm2) cudaFree(g->norm2);
     if (g->alive) cudaFree(g->alive);
-    g->g16 = nullptr; g->g32 = nullptr; g->norm2 = nullptr; g->alive = nullptr;
+    if (g->seq) cudaFree(g->seq);
+    g->g16 = nullptr; g->g32 = nullptr; g->norm2 = nullptr; g->alive = nullptr; g->seq = nullptr;
+    g->tmap_valid = false;
 }
 
 static int alloc_buffers(int dimp, uint64_t cap, __half** g16, float** g32, float** norm2,
@@ -130,6 +158,16 @@ static int alloc_buffers(int dimp, uint64_t cap, __half** g16, float** g32, floa
         cudaGetLastError();
         return FRP_E_NOMEM;
     }
+    // rows beyond `rows` are streamed by the last tcgen05 tile (its TMA box is bounded by the
+    // capacity, not by the row count): keep them finite
+    if (cudaMemset(*g16, 0, cap * dimp * sizeof(__half)) != cudaSuccess ||
+        cudaMemset(*norm2, 0, (cap + 256) * sizeof(float)) != cudaSuccess) {
+        set_error("gallery clear failed");
+        cudaFree(*g16); cudaFree(*g32); cudaFree(*norm2); cudaFree(*alive);
+        *g16 = nullptr; *g32 = nullptr; *norm2 = nullptr; *alive = nullptr;
+        cudaGetLastError();
+        return FRP_E_CUDA;
+    }
     return FRP_OK;
 }
 
@@ -141,6 +179,16 @@ static int ensure_capacity(frp_gallery* g, uint64_t need) {
     __half* n16; float* n32; float* nn; uint8_t* na;
     int rc = alloc_buffers(g->dimp, cap, &n16, &n32, &nn, &na);
     if (rc) return rc;
+    uint64_t* nseq = nullptr;
+    if (g->seq) {
+        if (cudaMalloc((void**)&nseq, cap * sizeof(uint64_t)) != cudaSuccess) {
+            cudaFree(n16); cudaFree(n32); cudaFree(nn); cudaFree(na);
+            set_error("gallery sequence allocation failed");
+            cudaGetLastError();
+            return FRP_E_NOMEM;
+        }
+        if (g->rows) FRP_CUDA(cudaMemcpy(nseq, g->seq, g->rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice));
+    }
     if (g->rows) {
         FRP_CUDA(cudaMemcpy(n16, g->g16, g->rows * g->dimp * sizeof(__half), cudaMemcpyDeviceToDevice));
         FRP_CUDA(cudaMemcpy(n32, g->g32, g->rows * g->dimp * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -148,26 +196,31 @@ static int ensure_capacity(frp_gallery* g, uint64_t need) {
         FRP_CUDA(cudaMemcpy(na, g->alive, g->rows, cudaMemcpyDeviceToDevice));
     }
     free_buffers(g);
-    g->g16 = n16; g->g32 = n32; g->norm2 = nn; g->alive = na;
+    g->g16 = n16; g->g32 = n32; g->norm2 = nn; g->alive = na; g->seq = nseq;
     g->capacity = cap;
+    gemm_refresh_maps(g);
     return FRP_OK;
 }
 
 // caller holds the unique lock; src is device fp32 [n][dim]
 static int ingest_device(frp_gallery* g, const float* src, uint64_t n, uint64_t first_row,
-                         cudaStream_t st) {
+                         cudaStream_t st, uint64_t src_stride = 0, bool verbatim = false) {
     if (n == 0) return FRP_OK;
     const int wpb = 8;
     const uint64_t blocks = (n + wpb - 1) / wpb;
-    ingest_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, g->dim, g->dimp, g->metric,
-                                                              first_row, g->g16, g->g32, g->norm2,
-                                                              g->alive, g->d_gmax);
+    const int normalise = (g->metric == FRP_METRIC_COS && !verbatim) ? 1 : 0;
+    ingest_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(src, n, g->dim, g->dimp,
+                                                              src_stride ? src_stride : (uint64_t)g->dim,
+                                                              normalise, first_row, g->g16, g->g32,
+                                                              g->norm2, g->alive, g->d_gmax);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }
 
 static int refresh_gmax(frp_gallery* g, cudaStream_t st) {
-    float both[2] = {0.f, 0.f};
+    // pinned landing zone behind the staging row: the copy is truly asynchronous and only
+    // `st` is waited for
+    float* both = g->h_stage + g->dim;
     FRP_CUDA(cudaMemcpyAsync(both, g->d_gmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     FRP_CUDA(cudaStreamSynchronize(st));
     g->gmax = both[0];
@@ -199,8 +252,27 @@ static int append_host_f32(frp_gallery* g, const float* rows, uint64_t n, uint64
     }
     if (stage) cudaFree(stage);
     g->rows += n;
+    g->h_alive.resize((size_t)g->rows, 1);
     if (first_row) *first_row = first;
     return refresh_gmax(g, 0);
+}
+
+// In-place update of one live row: pinned staging row -> one 4*dim-byte H2D, the ingest kernel
+// and the 8-byte bound read-back, all on the gallery's private stream.  No allocation, no
+// device-wide synchronisation; matchers that hold the shared lock have returned (host API) or
+// are ordered by their caller (device API) before the unique lock is granted.
+template <typename T>
+static int update_row(frp_gallery* g, uint64_t row, const T* vec) {
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
+    if (!g->h_alive[(size_t)row]) { set_error("row %llu is deleted", (unsigned long long)row); return FRP_E_RANGE; }
+    DeviceGuard dg(g->device);
+    for (int i = 0; i < g->dim; ++i) g->h_stage[i] = (float)vec[i];
+    FRP_CUDA(cudaMemcpyAsync(g->d_stage, g->h_stage, (size_t)g->dim * sizeof(float), cudaMemcpyHostToDevice,
+                             g->mut_stream));
+    int rc = ingest_device(g, g->d_stage, 1, row, g->mut_stream);
+    if (rc) return rc;
+    return refresh_gmax(g, g->mut_stream);
 }
 
 }  // namespace frp
@@ -270,12 +342,21 @@ int frp_gallery_create(int device, int dim, int metric, uint64_t capacity, frp_g
     g->capacity = capacity;
     cudaError_t e = cudaMalloc((void**)&g->d_gmax, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(g->d_gmax, 0, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->mut_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&g->h_stage, (size_t)(dim + 2) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_stage, (size_t)dim * sizeof(float));
     if (e != cudaSuccess) {
         set_error("gallery scalar allocation failed: %s", cudaGetErrorString(e));
         free_buffers(g);
+        if (g->d_gmax) cudaFree(g->d_gmax);
+        if (g->mut_stream) cudaStreamDestroy(g->mut_stream);
+        if (g->h_stage) cudaFreeHost(g->h_stage);
+        if (g->d_stage) cudaFree(g->d_stage);
         delete g;
+        cudaGetLastError();
         return FRP_E_CUDA;
     }
+    gemm_refresh_maps(g);
     *out = g;
     return FRP_OK;
 }
@@ -283,10 +364,18 @@ int frp_gallery_create(int device, int dim, int metric, uint64_t capacity, frp_g
 int frp_gallery_destroy(frp_gallery_t* g) {
     if (!g) return FRP_OK;
     {
+        // wait for every matcher that still holds the shared lock, then for the device work
+        // they queued; the caller must not use the handle afterwards
+        std::unique_lock<std::shared_mutex> lk(g->mu);
         DeviceGuard dg(g->device);
         cudaDeviceSynchronize();
         free_buffers(g);
         if (g->d_gmax) cudaFree(g->d_gmax);
+        if (g->d_stage) cudaFree(g->d_stage);
+        if (g->h_stage) cudaFreeHost(g->h_stage);
+        if (g->mut_stream) cudaStreamDestroy(g->mut_stream);
+        g->d_gmax = nullptr; g->d_stage = nullptr; g->h_stage = nullptr; g->mut_stream = nullptr;
+        cudaGetLastError();
     }
     delete g;
     return FRP_OK;
@@ -320,27 +409,9 @@ int frp_gallery_append_device(frp_gallery_t* g, const float* rows_dev, uint64_t 
     int rc = ingest_device(g, rows_dev, n, first, st);
     if (rc) return rc;
     g->rows += n;
+    g->h_alive.resize((size_t)g->rows, 1);
     if (first_row) *first_row = first;
     return refresh_gmax(g, st);
-}
-
-static int update_row(frp_gallery_t* g, uint64_t row, const float* vec) {
-    std::unique_lock<std::shared_mutex> lk(g->mu);
-    if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
-    DeviceGuard dg(g->device);
-    uint8_t a = 0;
-    FRP_CUDA(cudaMemcpy(&a, g->alive + row, 1, cudaMemcpyDeviceToHost));
-    if (!a) { set_error("row %llu is deleted", (unsigned long long)row); return FRP_E_RANGE; }
-    float* stage = nullptr;
-    FRP_CUDA(cudaMalloc((void**)&stage, g->dim * sizeof(float)));
-    cudaError_t e = cudaMemcpy(stage, vec, g->dim * sizeof(float), cudaMemcpyHostToDevice);
-    int rc = FRP_OK;
-    if (e != cudaSuccess) { set_error("H2D failed: %s", cudaGetErrorString(e)); rc = FRP_E_CUDA; }
-    if (!rc) rc = ingest_device(g, stage, 1, row, 0);
-    cudaStreamSynchronize(0);
-    cudaFree(stage);
-    if (rc) return rc;
-    return refresh_gmax(g, 0);
 }
 
 int frp_gallery_update_f32(frp_gallery_t* g, uint64_t row, const float* vec) {
@@ -349,21 +420,18 @@ int frp_gallery_update_f32(frp_gallery_t* g, uint64_t row, const float* vec) {
 }
 int frp_gallery_update_f64(frp_gallery_t* g, uint64_t row, const double* vec) {
     if (!g || !vec) { set_error("frp_gallery_update_f64: null argument"); return FRP_E_INVALID; }
-    std::vector<float> tmp(g->dim);
-    for (int i = 0; i < g->dim; ++i) tmp[i] = (float)vec[i];
-    return update_row(g, row, tmp.data());
+    return update_row(g, row, vec);
 }
 
 int frp_gallery_remove(frp_gallery_t* g, uint64_t row) {
     if (!g) { set_error("frp_gallery_remove: null gallery"); return FRP_E_INVALID; }
     std::unique_lock<std::shared_mutex> lk(g->mu);
     if (row >= g->rows) { set_error("row %llu out of range", (unsigned long long)row); return FRP_E_RANGE; }
+    if (!g->h_alive[(size_t)row]) { set_error("row %llu already deleted", (unsigned long long)row); return FRP_E_RANGE; }
     DeviceGuard dg(g->device);
-    uint8_t a = 0;
-    FRP_CUDA(cudaMemcpy(&a, g->alive + row, 1, cudaMemcpyDeviceToHost));
-    if (!a) { set_error("row %llu already deleted", (unsigned long long)row); return FRP_E_RANGE; }
-    FRP_CUDA(cudaMemset(g->alive + row, 0, 1));
-    FRP_CUDA(cudaDeviceSynchronize());
+    FRP_CUDA(cudaMemsetAsync(g->alive + row, 0, 1, g->mut_stream));
+    FRP_CUDA(cudaStreamSynchronize(g->mut_stream));
+    g->h_alive[(size_t)row] = 0;
     g->dead += 1;
     return FRP_OK;
 }
@@ -395,6 +463,22 @@ int frp_gallery_set_base(frp_gallery_t* g, uint64_t base_row) {
     return FRP_OK;
 }
 
+int frp_gallery_set_seq(frp_gallery_t* g, uint64_t first_row, uint64_t n, const uint64_t* seq) {
+    if (!g || (!seq && n)) { set_error("frp_gallery_set_seq: null argument"); return FRP_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lk(g->mu);
+    if (first_row + n > g->rows) { set_error("frp_gallery_set_seq: rows [%llu, %llu) out of range", (unsigned long long)first_row, (unsigned long long)(first_row + n)); return FRP_E_RANGE; }
+    DeviceGuard dg(g->device);
+    if (!g->seq) {
+        // first use: every existing row gets its default sequence base_row + row
+        FRP_CUDA(cudaMalloc((void**)&g->seq, g->capacity * sizeof(uint64_t)));
+        std::vector<uint64_t> init((size_t)g->rows);
+        for (uint64_t r = 0; r < g->rows; ++r) init[(size_t)r] = g->base_row + r;
+        if (g->rows) FRP_CUDA(cudaMemcpy(g->seq, init.data(), g->rows * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    if (n) FRP_CUDA(cudaMemcpy(g->seq + first_row, seq, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return FRP_OK;
+}
+
 int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, frp_gallery_t** out) {
     if (!g || !out || (!idx && n)) { set_error("frp_gallery_gather: null argument"); return FRP_E_INVALID; }
     std::shared_lock<std::shared_mutex> lk(g->mu);
@@ -404,6 +488,15 @@ int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, 
     int rc = frp_gallery_create(g->device, g->dim, g->metric, n, &ng);
     if (rc) return rc;
     DeviceGuard dg(g->device);
+    if (g->seq) {
+        if (cudaMalloc((void**)&ng->seq, ng->capacity * sizeof(uint64_t)) != cudaSuccess) {
+            set_error("gather: sequence allocation failed");
+            frp_gallery_destroy(ng);
+            cudaGetLastError();
+            return FRP_E_NOMEM;
+        }
+    }
+    ng->base_row = g->base_row;
     if (n) {
         uint64_t* didx = nullptr;
         FRP_CUDA(cudaMalloc((void**)&didx, n * sizeof(uint64_t)));
@@ -411,7 +504,8 @@ int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, 
         if (e == cudaSuccess) {
             const int wpb = 8;
             gather_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32>>>(
-                g->g32, g->g16, g->norm2, didx, n, g->dimp, ng->g32, ng->g16, ng->norm2, ng->alive);
+                g->g32, g->g16, g->norm2, didx, n, g->dimp, ng->g32, ng->g16, ng->norm2, ng->alive, g->seq,
+                ng->seq);
             e = cudaGetLastError();
             count_launch();
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -424,6 +518,7 @@ int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, 
         }
     }
     ng->rows = n;
+    ng->h_alive.assign((size_t)n, 1);
     ng->gmax = g->gmax;
     ng->gerr = g->gerr;
     const float both[2] = {ng->gmax, ng->gerr};
@@ -454,8 +549,11 @@ int frp_gallery_save(const frp_gallery_t* g, const char* path) {
     if (!g || !path) { set_error("frp_gallery_save: null argument"); return FRP_E_INVALID; }
     std::shared_lock<std::shared_mutex> lk(g->mu);
     DeviceGuard dg(g->device);
-    FILE* f = fopen(path, "wb");
-    if (!f) { set_error("cannot open %s for writing", path); return FRP_E_IO; }
+    // written next to the target and renamed over it: a crash mid-save never leaves a
+    // truncated snapshot under the final name
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_error("cannot open %s for writing", tmp.c_str()); return FRP_E_IO; }
     SnapshotHeader h;
     memset(&h, 0, sizeof(h));
     memcpy(h.magic, "FRPGAL1", 8);
@@ -470,13 +568,11 @@ int frp_gallery_save(const frp_gallery_t* g, const char* path) {
                        cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
         ok = fwrite(buf.data(), sizeof(float), (size_t)m * g->dimp, f) == (size_t)m * g->dimp;
     }
-    std::vector<uint8_t> al((size_t)g->rows);
-    if (ok && g->rows) {
-        ok = cudaMemcpy(al.data(), g->alive, g->rows, cudaMemcpyDeviceToHost) == cudaSuccess &&
-             fwrite(al.data(), 1, al.size(), f) == al.size();
-    }
-    fclose(f);
-    if (!ok) { set_error("write to %s failed", path); cudaGetLastError(); return FRP_E_IO; }
+    if (ok && g->rows) ok = fwrite(g->h_alive.data(), 1, (size_t)g->rows, f) == (size_t)g->rows;
+    ok = (fflush(f) == 0) && ok;
+    ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), path) == 0;
+    if (!ok) { remove(tmp.c_str()); set_error("write to %s failed", path); cudaGetLastError(); return FRP_E_IO; }
     return FRP_OK;
 }
 
@@ -490,37 +586,58 @@ int frp_gallery_load(int device, const char* path, frp_gallery_t** out) {
         set_error("%s is not a gallery snapshot", path);
         return FRP_E_IO;
     }
+    // the header is untrusted input: every field is checked against what this library would
+    // have written, and the payload size against the file, before anything is allocated
+    bool sane = h.dim > 0 && h.dim <= 512 && h.dimp == pad_dim(h.dim) &&
+                (h.metric == FRP_METRIC_L2 || h.metric == FRP_METRIC_COS) && h.dead <= h.rows &&
+                h.rows < (1ull << 40);
+    if (sane) {
+        const uint64_t expect = sizeof(h) + h.rows * (uint64_t)h.dimp * sizeof(float) + h.rows;
+        sane = fseek(f, 0, SEEK_END) == 0 && (uint64_t)ftell(f) == expect &&
+               fseek(f, (long)sizeof(h), SEEK_SET) == 0;
+    }
+    if (!sane) {
+        fclose(f);
+        set_error("%s: corrupt or truncated snapshot header (dim=%d dimp=%d metric=%d rows=%llu)", path, h.dim,
+                  h.dimp, h.metric, (unsigned long long)h.rows);
+        return FRP_E_IO;
+    }
     frp_gallery_t* g = nullptr;
     int rc = frp_gallery_create(device, h.dim, h.metric, h.rows, &g);
     if (rc) { fclose(f); return rc; }
     DeviceGuard dg(device);
-    // rows are stored as the (already normalised) fp32 master padded to dimp;
-    // re-ingest reproduces g16 / norm2 bit-identically (normalising a unit row is
-    // not idempotent in fp32, so the master is uploaded verbatim afterwards).
+    // rows are stored as the fp32 master padded to dimp (COS: already normalised).  They are
+    // ingested VERBATIM: the fp16 copy, |g|^2 and the measured rounding error of the
+    // certificate are all derived from exactly the master that is stored.
     const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * h.dimp));
-    std::vector<float> buf((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(h.rows, 1)) * h.dimp);
-    std::vector<float> packed;
-    bool ok = true;
+    const uint64_t nbuf = std::min<uint64_t>(chunk, std::max<uint64_t>(h.rows, 1));
+    std::vector<float> buf((size_t)nbuf * h.dimp);
+    float* stage = nullptr;
+    bool ok = cudaMalloc((void**)&stage, (size_t)nbuf * h.dimp * sizeof(float)) == cudaSuccess;
     for (uint64_t lo = 0; ok && lo < h.rows; lo += chunk) {
         const uint64_t m = std::min(chunk, h.rows - lo);
         ok = fread(buf.data(), sizeof(float), (size_t)m * h.dimp, f) == (size_t)m * h.dimp;
         if (!ok) break;
-        packed.resize((size_t)m * h.dim);
-        for (uint64_t r = 0; r < m; ++r)
-            memcpy(&packed[(size_t)r * h.dim], &buf[(size_t)r * h.dimp], h.dim * sizeof(float));
-        uint64_t first = 0;
-        rc = frp_gallery_append_f32(g, packed.data(), m, &first);
-        if (rc) { fclose(f); frp_gallery_destroy(g); return rc; }
-        ok = cudaMemcpy(g->g32 + lo * h.dimp, buf.data(), m * h.dimp * sizeof(float),
-                        cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = cudaMemcpy(stage, buf.data(), m * h.dimp * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok) ok = ingest_device(g, stage, m, lo, 0, (uint64_t)h.dimp, true) == FRP_OK;
+        if (ok) ok = cudaStreamSynchronize(0) == cudaSuccess;
     }
-    std::vector<uint8_t> al((size_t)h.rows);
+    if (stage) cudaFree(stage);
+    g->rows = h.rows;
+    g->h_alive.assign((size_t)h.rows, 1);
+    uint64_t dead = 0;
     if (ok && h.rows) {
-        ok = fread(al.data(), 1, al.size(), f) == al.size() &&
-             cudaMemcpy(g->alive, al.data(), h.rows, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = fread(g->h_alive.data(), 1, (size_t)h.rows, f) == (size_t)h.rows &&
+             cudaMemcpy(g->alive, g->h_alive.data(), h.rows, cudaMemcpyHostToDevice) == cudaSuccess;
+        for (uint64_t r = 0; ok && r < h.rows; ++r) {
+            g->h_alive[(size_t)r] = g->h_alive[(size_t)r] ? 1 : 0;
+            dead += g->h_alive[(size_t)r] ? 0 : 1;
+        }
     }
     fclose(f);
-    if (!ok) { set_error("read of %s failed", path); frp_gallery_destroy(g); cudaGetLastError(); return FRP_E_IO; }
+    if (ok && dead != h.dead) { ok = false; }
+    if (ok) ok = refresh_gmax(g, 0) == FRP_OK;
+    if (!ok) { set_error("read of %s failed (I/O error or inconsistent tombstones)", path); frp_gallery_destroy(g); cudaGetLastError(); return FRP_E_IO; }
     g->dead = h.dead;
     g->base_row = h.base_row;
     *out = g;

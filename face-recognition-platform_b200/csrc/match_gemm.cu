@@ -245,25 +245,38 @@ __device__ __forceinline__ void epilogue_warps(const GemmArgs& a, const int warp
             }
             const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             if (mx >= cut) {
+                // Rare path, taken by the whole warp when any lane has a candidate: test the four
+                // max chains first so that only the 8 scores of a chain that can hold a candidate
+                // are walked (a gallery with real matches takes this path for ~10 % of the
+                // 32-score groups; walking all 32 scores each time cost 40 % of the kernel).
+                // Insertion order is chain-major, not column-major: ties at the tail of a full
+                // list may therefore drop the lower row, which the certificate (strict
+                // s_kth > L + eps) turns into a fallback, never into a wrong answer.
+                const float mch[4] = {m0, m1, m2, m3};
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = sv[j];
-                    const uint32_t row = row0 + c + j;
-                    if (s >= cut && row < a.rows) {
-                        if (a.alive[row]) {
-                            float cs = s;
-                            uint32_t cr = row;
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (mch[ch] >= cut) {
 #pragma unroll
-                            for (int p = 0; p < KP; ++p) {
-                                const bool gt = cs > ls[p];
-                                const float ts = gt ? ls[p] : cs;
-                                const uint32_t tr = gt ? lr[p] : cr;
-                                ls[p] = gt ? cs : ls[p];
-                                lr[p] = gt ? cr : lr[p];
-                                cs = ts;
-                                cr = tr;
+                        for (int j = ch; j < 32; j += 4) {
+                            const float s = sv[j];
+                            const uint32_t row = row0 + c + j;
+                            if (s >= cut && row < a.rows) {
+                                if (a.alive[row]) {
+                                    float cs = s;
+                                    uint32_t cr = row;
+#pragma unroll
+                                    for (int p = 0; p < KP; ++p) {
+                                        const bool gt = cs > ls[p];
+                                        const float ts = gt ? ls[p] : cs;
+                                        const uint32_t tr = gt ? lr[p] : cr;
+                                        ls[p] = gt ? cs : ls[p];
+                                        lr[p] = gt ? cr : lr[p];
+                                        cs = ts;
+                                        cr = tr;
+                                    }
+                                    cut = fmaxf(cut0, ls[KP - 1]);
+                                }
                             }
-                            cut = fmaxf(cut0, ls[KP - 1]);
                         }
                     }
                 }
@@ -654,7 +667,7 @@ static bool use_pair_kernel(const frp_gallery* g) { return g_gemm_pair < 0 ? g->
 
 bool gemm_supported(const frp_gallery* g) {
     return (g->dimp % kBlockK) == 0 && g->dimp <= 512 && g->rows > 0 && g->rows < (1ull << 31) &&
-           get_encode_fn() != nullptr;
+           g->tmap_valid;
 }
 
 static int gemm_groups(int B) { return (B + kTileM - 1) / kTileM; }
@@ -681,20 +694,37 @@ int gemm_num_lists(const frp_gallery* g, int B) {
     return per * gemm_lpc(g);
 }
 
-int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int B, int KP, uint64_t* cand,
+// Descriptors of the fp16 scan copy over its whole CAPACITY: they only change when the buffers
+// are reallocated (unique lock), so a match never encodes a gallery map.  Rows in
+// [rows, capacity) are zero (alloc_buffers clears the copy) and masked by `row < rows`.
+void gemm_refresh_maps(frp_gallery* g) {
+    g->tmap_valid = false;
+    if ((g->dimp % kBlockK) != 0 || g->dimp > 512 || !g->g16 || !get_encode_fn()) return;
+    CUtensorMap tg, tgh;
+    if (encode_map(&tg, g->g16, g->capacity, g->dimp, kTileN)) return;
+    if (encode_map(&tgh, g->g16, g->capacity, g->dimp, kTileN / 2)) return;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(g->tmap_g, &tg, sizeof(tg));
+    memcpy(g->tmap_gh, &tgh, sizeof(tgh));
+    g->tmap_valid = true;
+}
+
+int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp) {
+    return encode_map(reinterpret_cast<CUtensorMap*>(tmap_out), q16, (uint64_t)groups * kTileM, dimp, kTileM);
+}
+
+int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int B, int KP, uint64_t* cand,
                       int nlists, cudaStream_t st) {
     const int groups = gemm_groups(B);
     const int nkb = g->dimp / kBlockK;
     const bool l2 = (g->metric == FRP_METRIC_L2);
     const int stages = pick_stages(nkb, l2);
     if (stages < 2) { set_error("match_gemm: not enough shared memory for dimp=%d", g->dimp); return FRP_E_UNSUPPORTED; }
-    CUtensorMap tq, tg, tgh;
-    int rc = encode_map(&tq, q16, (uint64_t)groups * kTileM, g->dimp, kTileM);
-    if (rc) return rc;
-    rc = encode_map(&tg, g->g16, g->rows, g->dimp, kTileN);
-    if (rc) return rc;
-    rc = encode_map(&tgh, g->g16, g->rows, g->dimp, kTileN / 2);   // half tiles for the cluster multicast
-    if (rc) return rc;
+    if (!g->tmap_valid) { set_error("match_gemm: gallery tensor maps unavailable"); return FRP_E_UNSUPPORTED; }
+    const CUtensorMap& tq = *reinterpret_cast<const CUtensorMap*>(tmap_q);
+    const CUtensorMap& tg = *reinterpret_cast<const CUtensorMap*>(g->tmap_g);
+    const CUtensorMap& tgh = *reinterpret_cast<const CUtensorMap*>(g->tmap_gh);
+    int rc = FRP_OK;
     // an even number of 128-query groups runs as clusters of two CTAs sharing every gallery tile
     const int cs = (groups % 2 == 0 && !g_gemm_no_cluster) ? 2 : 1;
     GemmArgs a;
@@ -739,12 +769,8 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
         attr[0].val.clusterDim.y = 1;
 #define FRP_PAIR_LAUNCH(KP_, L2_, LPC_)                                                                  \
     {                                                                                                    \
-        static thread_local size_t configured = 0;                                                       \
-        if (configured < psmem) {                                                                        \
-            FRP_CUDA(cudaFuncSetAttribute(match_gemm_pair_kernel<KP_, L2_, LPC_>,                        \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));     \
-            configured = psmem;                                                                          \
-        }                                                                                                \
+        configure_func_smem((const void*)match_gemm_pair_kernel<KP_, L2_, LPC_>, g->device, psmem, &rc); \
+        if (rc) return rc;                                                                               \
         le = cudaLaunchKernelEx(&cfg, match_gemm_pair_kernel<KP_, L2_, LPC_>, tq, tgh, a);               \
     }
         if (KP != 16 && KP != 32) { set_error("match_gemm: unsupported KP=%d", KP); return FRP_E_UNSUPPORTED; }
@@ -770,12 +796,8 @@ int launch_match_gemm(frp_gallery* g, const __half* q16, const QParams* qp, int 
     }
 #define FRP_GEMM_LAUNCH(KP_, L2_, CS_, LPC_)                                                             \
     {                                                                                                    \
-        static thread_local size_t configured = 0;                                                       \
-        if (configured < smem) {                                                                         \
-            FRP_CUDA(cudaFuncSetAttribute(match_gemm_kernel<KP_, L2_, CS_, LPC_>,                        \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-            configured = smem;                                                                           \
-        }                                                                                                \
+        configure_func_smem((const void*)match_gemm_kernel<KP_, L2_, CS_, LPC_>, g->device, smem, &rc);  \
+        if (rc) return rc;                                                                               \
         le = cudaLaunchKernelEx(&cfg, match_gemm_kernel<KP_, L2_, CS_, LPC_>, tq, tg, tgh, a);           \
     }
 #define FRP_GEMM_CASES(LPC_)                                 \

@@ -14,7 +14,7 @@ namespace frp {
 
 namespace {
 
-constexpr int kRCap = 128;          // max survivors re-ranked per query
+constexpr int kRCap = 256;          // max survivors re-ranked per query (k <= 64 plus the 2-eps band)
 constexpr int kRerankThreads = 256;
 
 __device__ __forceinline__ float float_round_down(double x) {
@@ -27,7 +27,8 @@ __device__ __forceinline__ float float_round_down(double x) {
 // eps_mode: 0 = fp16 gallery x fp32 query (scan), 1 = fp16 x fp16 (tcgen05), 2 = fp32 master
 // scan.  The prefilter error bound is rigorous at any scale (Cauchy-Schwarz on the MEASURED
 // rounding errors): |s~ - s| <= |g16-g|*|q16| + |g|*|q16-q| + fp32 accumulation.
-__global__ void prep_queries_kernel(const float* __restrict__ q, int dim, int dimp, int metric,
+__global__ void prep_queries_kernel(const float* __restrict__ q, size_t qstride,
+                                    const uint64_t* __restrict__ q_rows, int dim, int dimp, int metric,
                                     double tau, int flags, int eps_mode, float gmax, float gerr,
                                     float* __restrict__ qprep, __half* __restrict__ q16,
                                     QParams* __restrict__ qp) {
@@ -35,7 +36,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int dim, int di
     __shared__ double red2[32];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const float* src = q + (size_t)b * dim;
+    const float* src = q + (q_rows ? (size_t)q_rows[b] : (size_t)b) * qstride;
     double acc = 0.0;
     for (int i = tid; i < dim; i += blockDim.x) {
         const double x = (double)src[i];
@@ -114,8 +115,10 @@ struct RerankArgs {
     int nlists, KP, k, dimp, metric, flags, npad;
     double tau;
     uint64_t base_row;
+    const uint64_t* seq;    // optional per-row global sequence (overrides base_row + row)
     int64_t* out_idx;
-    float* out_score;
+    float* out_score;       // optional
+    double* out_score64;    // optional (shard record: the merge ranks on the exact value)
     int32_t* out_count;
     int32_t* out_status;
 };
@@ -249,15 +252,17 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs
         for (int c = 0; c < m; ++c)
             if (c != tid && ex_pass[c] && better(a.metric, ex_v[c], ex_row[c], v, r)) ++rank;
         if (rank < k) {
-            a.out_idx[(size_t)b * k + rank] = (int64_t)(a.base_row + r);
-            a.out_score[(size_t)b * k + rank] = (float)v;
+            a.out_idx[(size_t)b * k + rank] = a.seq ? (int64_t)a.seq[r] : (int64_t)(a.base_row + r);
+            if (a.out_score) a.out_score[(size_t)b * k + rank] = (float)v;
+            if (a.out_score64) a.out_score64[(size_t)b * k + rank] = v;
             if (rank == k - 1) s_kth = ex_s[tid];
         }
     }
     const int cnt = npass < k ? npass : k;
     for (int i = cnt + tid; i < k; i += blockDim.x) {
         a.out_idx[(size_t)b * k + i] = -1;
-        a.out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+        if (a.out_score) a.out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+        if (a.out_score64) a.out_score64[(size_t)b * k + i] = __longlong_as_double(0x7ff8000000000000ll);
     }
     __syncthreads();
 
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs
 // ---------------------------------------------------------------------------
 __global__ void scores_kernel(const float* __restrict__ g32, const uint8_t* __restrict__ alive,
                               const float* __restrict__ qprep, uint64_t rows, int dimp, int B,
-                              int metric, double* __restrict__ out) {
+                              int metric, double* __restrict__ out, uint64_t out_stride) {
     const int lane = threadIdx.x & 31;
     const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -309,7 +314,7 @@ __global__ void scores_kernel(const float* __restrict__ g32, const uint8_t* __re
         if (lane == 0) {
             double v = (metric == FRP_METRIC_COS) ? acc : sqrt(acc);
             if (!live) v = __longlong_as_double(0x7ff8000000000000ll);   // NaN marks tombstones
-            out[(size_t)b * rows + row] = v;
+            out[(size_t)b * out_stride + row] = v;
         }
     }
 }
@@ -325,9 +330,10 @@ __global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t
                                   const uint8_t* __restrict__ in_count_b,
                                   const uint8_t* __restrict__ in_status_b, size_t rank_stride,
                                   int64_t* __restrict__ out_idx, float* __restrict__ out_score,
-                                  int32_t* __restrict__ out_count, int32_t* __restrict__ out_any_status) {
+                                  double* __restrict__ out_score64, int32_t* __restrict__ out_count,
+                                  int32_t* __restrict__ out_any_status) {
     __shared__ int64_t s_idx[kMergeMax];
-    __shared__ float s_sc[kMergeMax];
+    __shared__ double s_sc[kMergeMax];
     __shared__ int s_n;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -339,7 +345,7 @@ __global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t
         const int32_t* cnt = reinterpret_cast<const int32_t*>(in_count_b + (size_t)r * rank_stride);
         if (j < cnt[b]) {
             const int64_t* idx = reinterpret_cast<const int64_t*>(in_idx_b + (size_t)r * rank_stride);
-            const float* sc = reinterpret_cast<const float*>(in_score_b + (size_t)r * rank_stride);
+            const double* sc = reinterpret_cast<const double*>(in_score_b + (size_t)r * rank_stride);
             const int pos = atomicAdd(&s_n, 1);
             s_idx[pos] = idx[(size_t)b * k + j];
             s_sc[pos] = sc[(size_t)b * k + j];
@@ -351,12 +357,14 @@ __global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t
     }
     __syncthreads();
     const int n = s_n;
+    // same comparator as rerank_kernel (float64 score, then global row): the merged order of R
+    // shards is exactly the order one gallery holding all rows would produce
     for (int e = tid; e < n; e += blockDim.x) {
-        const float v = s_sc[e];
+        const double v = s_sc[e];
         const int64_t id = s_idx[e];
         int rank = 0;
         for (int c = 0; c < n; ++c) {
-            const float vc = s_sc[c];
+            const double vc = s_sc[c];
             const int64_t ic = s_idx[c];
             const bool bt = (metric == FRP_METRIC_COS) ? (vc > v || (vc == v && ic < id))
                                                        : (vc < v || (vc == v && ic < id));
@@ -364,13 +372,15 @@ __global__ void merge_topk_kernel(int metric, int R, int B, int k, const uint8_t
         }
         if (rank < k) {
             out_idx[(size_t)b * k + rank] = id;
-            out_score[(size_t)b * k + rank] = v;
+            if (out_score) out_score[(size_t)b * k + rank] = (float)v;
+            if (out_score64) out_score64[(size_t)b * k + rank] = v;
         }
     }
     const int cnt = n < k ? n : k;
     for (int i = cnt + tid; i < k; i += blockDim.x) {
         out_idx[(size_t)b * k + i] = -1;
-        out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+        if (out_score) out_score[(size_t)b * k + i] = __int_as_float(0x7fc00000);
+        if (out_score64) out_score64[(size_t)b * k + i] = __longlong_as_double(0x7ff8000000000000ll);
     }
     if (tid == 0) out_count[b] = cnt;
 }
@@ -406,7 +416,7 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
                   float* __restrict__ out_score, int32_t* __restrict__ out_count,
                   int32_t* __restrict__ out_any_status) {
     __shared__ int64_t s_idx[kMergeMax];
-    __shared__ float s_sc[kMergeMax];
+    __shared__ double s_sc[kMergeMax];
     __shared__ int s_n;
     __shared__ bool s_last;
     const int tid = threadIdx.x;
@@ -454,7 +464,7 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
     __syncthreads();
 
     // ---- merge ----
-    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 4, o3 = o2 + (size_t)B * 4;
+    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 8, o3 = o2 + (size_t)B * 4;
     const uint8_t* recv = mine + kExchHeader + (size_t)par * R * rec_bytes;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         if (tid == 0) s_n = 0;
@@ -467,7 +477,7 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
             if (j < cnt[b]) {
                 const int pos = atomicAdd(&s_n, 1);
                 s_idx[pos] = reinterpret_cast<const int64_t*>(rec)[(size_t)b * k + j];
-                s_sc[pos] = reinterpret_cast<const float*>(rec + o1)[(size_t)b * k + j];
+                s_sc[pos] = reinterpret_cast<const double*>(rec + o1)[(size_t)b * k + j];
             }
         }
         if (out_any_status && tid < R) {
@@ -477,11 +487,11 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
         __syncthreads();
         const int n = s_n;
         for (int e = tid; e < n; e += blockDim.x) {
-            const float v = s_sc[e];
+            const double v = s_sc[e];
             const int64_t id = s_idx[e];
             int rk = 0;
             for (int c = 0; c < n; ++c) {
-                const float vc = s_sc[c];
+                const double vc = s_sc[c];
                 const int64_t ic = s_idx[c];
                 const bool bt = (metric == FRP_METRIC_COS) ? (vc > v || (vc == v && ic < id))
                                                            : (vc < v || (vc == v && ic < id));
@@ -489,7 +499,7 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
             }
             if (rk < k) {
                 out_idx[(size_t)b * k + rk] = id;
-                out_score[(size_t)b * k + rk] = v;
+                out_score[(size_t)b * k + rk] = (float)v;
             }
         }
         const int cntb = n < k ? n : k;
@@ -504,20 +514,22 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
 
 }  // namespace
 
-int launch_prep_queries(const frp_gallery* g, const float* q_dev, int B, double tau, int flags,
-                        int eps_mode, float* qprep, __half* q16, QParams* qp, cudaStream_t st) {
-    prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, g->dim, g->dimp, g->metric, tau, flags, eps_mode,
-                                           g->gmax, g->gerr, qprep, q16, qp);
+int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride, const uint64_t* q_rows,
+                        int B, double tau, int flags, int eps_mode, float* qprep, __half* q16,
+                        QParams* qp, cudaStream_t st) {
+    prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, qstride, q_rows, g->dim, g->dimp, g->metric, tau, flags,
+                                           eps_mode, g->gmax, g->gerr, qprep, q16, qp);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }
 
-int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, cudaStream_t st) {
+int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, uint64_t out_stride,
+                  cudaStream_t st) {
     if (g->rows == 0) return FRP_OK;
     const int wpb = 8;
     const uint64_t blocks = (g->rows + wpb - 1) / wpb;
     scores_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(g->g32, g->alive, qprep, g->rows, g->dimp, B,
-                                                         g->metric, out);
+                                                         g->metric, out, out_stride);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }
@@ -525,7 +537,8 @@ int launch_scores(const frp_gallery* g, const float* qprep, int B, double* out, 
 // tau travels separately from QParams so the exact comparison uses the caller's double
 int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, int B, int k, int KP,
                   int flags, double tau, const uint64_t* cand, int nlists, int64_t* out_idx,
-                  float* out_score, int32_t* out_count, int32_t* out_status, cudaStream_t st) {
+                  float* out_score, double* out_score64, int32_t* out_count, int32_t* out_status,
+                  cudaStream_t st) {
     RerankArgs a;
     a.g32 = g->g32;
     a.qprep = qprep;
@@ -539,8 +552,10 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
     a.flags = flags;
     a.tau = tau;
     a.base_row = g->base_row;
+    a.seq = g->seq;
     a.out_idx = out_idx;
     a.out_score = out_score;
+    a.out_score64 = out_score64;
     a.out_count = out_count;
     a.out_status = out_status;
     int npad = 1;
@@ -551,11 +566,10 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
         set_error("rerank: %d candidate slots exceed shared memory", nlists * KP);
         return FRP_E_UNSUPPORTED;
     }
-    static thread_local size_t configured = 0;
-    if (smem > 40 * 1024 && configured < smem) {
-        FRP_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured = smem;
+    if (smem > 32 * 1024) {
+        int rc = FRP_OK;
+        configure_func_smem((const void*)rerank_kernel, g->device, smem, &rc);
+        if (rc) return rc;
     }
     rerank_kernel<<<B, kRerankThreads, smem, st>>>(a);
     FRP_CHECK_LAUNCH();
@@ -567,9 +581,7 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
 extern "C" {
 
 size_t frp_exchange_buffer_bytes(int R, int B, int k) {
-    size_t rec = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
-    rec = (rec + 15) / 16 * 16;
-    return (size_t)frp::kExchHeader + 2 * (size_t)R * rec;
+    return (size_t)frp::kExchHeader + 2 * (size_t)R * frp_shard_record_bytes(B, k);
 }
 
 int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void* send_record,
@@ -582,13 +594,14 @@ int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void*
         set_error("frp_push_merge_device: invalid argument (R=%d rank=%d B=%d k=%d)", R, rank, B, k);
         return FRP_E_INVALID;
     }
-    size_t rec = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
-    rec = (rec + 15) / 16 * 16;
+    const size_t rec = frp_shard_record_bytes(B, k);
     cudaStream_t st = (cudaStream_t)stream;
     if (out_any_status) FRP_CUDA(cudaMemsetAsync(out_any_status, 0, sizeof(int32_t), st));
-    // every block must be resident at once (blocks spin on flags written by other GPUs,
-    // and the flags are only published once all local blocks have pushed)
-    int grid = B < 296 ? B : 296;
+    // Blocks spin on flags written by OTHER GPUs; the local pushes they depend on are done by the
+    // lowest-numbered blocks, which never wait before pushing.  The grid is kept below one
+    // block per SM (148) so every block is resident even when another stream (alignment) holds
+    // part of each SM, and a peer that never arrives ends in the 3 s timeout flag, not a hang.
+    int grid = B < 128 ? B : 128;
     push_merge_kernel<<<grid, 128, 0, st>>>(metric, R, rank, B, k, (const uint8_t*)send_record,
                                             (uint8_t* const*)peers_dev, rec, epoch, counter_dev, out_idx,
                                             out_score, out_count, out_any_status);
@@ -597,26 +610,27 @@ int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void*
 }
 
 size_t frp_shard_record_bytes(int B, int k) {
-    size_t n = (size_t)B * k * 8 + (size_t)B * k * 4 + (size_t)B * 4 + (size_t)B * 4;
+    // idx i64 | score f64 | count i32 | status i32
+    size_t n = (size_t)B * k * 8 + (size_t)B * k * 8 + (size_t)B * 4 + (size_t)B * 4;
     return (n + 15) / 16 * 16;
 }
 
 int frp_merge_packed_device(int metric, int R, int B, int k, const void* records, int64_t* out_idx,
-                            float* out_score, int32_t* out_count, int32_t* out_any_status,
-                            void* stream) {
+                            float* out_score, double* out_score64, int32_t* out_count,
+                            int32_t* out_any_status, void* stream) {
     using namespace frp;
-    if (R <= 0 || B <= 0 || k <= 0 || R * k > kMergeMax || R > 128 || !records || !out_idx || !out_score ||
-        !out_count) {
+    if (R <= 0 || B <= 0 || k <= 0 || R * k > kMergeMax || R > 128 || !records || !out_idx ||
+        (!out_score && !out_score64) || !out_count) {
         set_error("frp_merge_packed_device: invalid argument (R=%d B=%d k=%d, R*k <= %d)", R, B, k, kMergeMax);
         return FRP_E_INVALID;
     }
     const size_t rec = frp_shard_record_bytes(B, k);
     const uint8_t* base = (const uint8_t*)records;
-    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 4, o3 = o2 + (size_t)B * 4;
+    const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 8, o3 = o2 + (size_t)B * 4;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_any_status) FRP_CUDA(cudaMemsetAsync(out_any_status, 0, sizeof(int32_t), st));
     merge_topk_kernel<<<B, 128, 0, st>>>(metric, R, B, k, base, base + o1, base + o2, base + o3, rec,
-                                         out_idx, out_score, out_count, out_any_status);
+                                         out_idx, out_score, out_score64, out_count, out_any_status);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }

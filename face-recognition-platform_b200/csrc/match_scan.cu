@@ -29,6 +29,7 @@ int launch_match_scan(const frp_gallery* g, bool use_master, const float* qprep,
     a.B = B;
     a.metric = g->metric;
     a.stages = 0;
+    a.device = g->device;
     switch (g->dimp) {
         case 64: return use_master ? scan_f32_64(a, B, KP, nlists, st) : scan_f16_64(a, B, KP, nlists, st);
         case 128: return use_master ? scan_f32_128(a, B, KP, nlists, st) : scan_f16_128(a, B, KP, nlists, st);

@@ -18,6 +18,7 @@ struct ScanArgs {
     int B;
     int metric;
     int stages;
+    int device;
 };
 
 #define FRP_SCAN_DECL(NAME) int NAME(const ScanArgs& a, int B, int KP, int nlists, cudaStream_t st);

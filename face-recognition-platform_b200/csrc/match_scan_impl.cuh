@@ -290,10 +290,10 @@ int launch_one(const ScanArgs& a, int nlists, int qgroups, cudaStream_t st) {
                         (size_t)kConsumerWarps * QB * CAP * sizeof(uint64_t) +
                         kConsumerWarps * QB * sizeof(int) + 16;
     auto kern = match_scan_kernel<T, DIMP, QB, KP>;
-    static thread_local size_t configured = 0;   // per instantiation & thread; cheap to repeat
-    if (configured < smem) {
-        FRP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    {
+        int rc = FRP_OK;
+        configure_func_smem((const void*)kern, a.device, smem, &rc);
+        if (rc) return rc;
     }
     ScanArgs b = a;
     b.stages = stages;

@@ -12,12 +12,13 @@ from ._capi import (FrpError, METRIC_COS, METRIC_L2, MATCH_FORCE_EXACT, MATCH_FO
 from .gallery import Gallery, GalleryDict
 from .face_service import FaceService
 from . import align
-from .camera_scan import scan_cameras
-from .shard import ShardedMatcher, shard_bounds, shard_streams
+from .camera_scan import BatchingMatcher, CooldownFilter, DeviceCooldown, scan_cameras, scan_cameras_recorded
+from .shard import CertifiedPipeline, ShardedGalleryDict, ShardedMatcher, shard_bounds, shard_streams
 
 __all__ = [
     "FrpError", "METRIC_COS", "METRIC_L2", "MATCH_FORCE_EXACT", "MATCH_FORCE_GEMM", "MATCH_FORCE_SCAN",
     "MATCH_NO_THRESHOLD", "MATCH_STRICT", "STATUS_OK", "STATUS_FALLBACK", "STATUS_UNCERTIFIED",
     "device_count", "kernel_launches", "last_match_path", "Gallery", "GalleryDict", "FaceService",
-    "align", "ShardedMatcher", "shard_bounds", "shard_streams", "scan_cameras",
+    "align", "ShardedMatcher", "ShardedGalleryDict", "CertifiedPipeline", "shard_bounds", "shard_streams",
+    "scan_cameras", "scan_cameras_recorded", "BatchingMatcher", "CooldownFilter", "DeviceCooldown",
 ]

@@ -62,12 +62,20 @@ SIGNATURES = {
     "frp_gallery_save": (_i, [_vp, C.c_char_p]),
     "frp_gallery_load": (_i, [_i, C.c_char_p, C.POINTER(_vp)]),
     "frp_gallery_set_base": (_i, [_vp, _u64]),
+    "frp_gallery_set_seq": (_i, [_vp, _u64, _u64, _vp]),
     "frp_match": (_i, [_vp, _vp, _i, _d, _i, _i, _vp, _vp, _vp, _vp]),
     "frp_match_device": (_i, [_vp, _vp, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "frp_scores": (_i, [_vp, _vp, _i, _vp]),
-    "frp_scores_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "frp_scores": (_i, [_vp, _vp, _i, _vp, _u64, _pu64]),
+    "frp_scores_device": (_i, [_vp, _vp, _i, _vp, _u64, _pu64, _vp]),
     "frp_shard_record_bytes": (_sz, [_i, _i]),
-    "frp_merge_packed_device": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frp_match_record_device": (_i, [_vp, _vp, _i, _d, _i, _i, _vp, _vp]),
+    "frp_merge_packed_device": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frp_cluster": (_i, [_vp, _d, _i, _vp, _u64, _pi, _vp]),
+    "frp_cooldown_create": (_i, [_i, _u64, C.POINTER(_vp)]),
+    "frp_cooldown_destroy": (_i, [_vp]),
+    "frp_cooldown_clear": (_i, [_vp, _vp]),
+    "frp_cooldown_filter_device": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
+    "frp_match_hits": (_i, [_vp, _vp, _vp, _i, _d, _i, _i, _vp, _vp, _d, _d, _vp, _pi]),
     "frp_exchange_buffer_bytes": (_sz, [_i, _i, _i]),
     "frp_push_merge_device": (_i, [_i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "frp_estimate_norm": (_i, [_vp, _i, _vp]),
@@ -85,6 +93,12 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+# frp_hit_t (include/frp_b200.h): one recorded detection
+HIT_DTYPE = np.dtype([("query", np.int32), ("rank", np.int32), ("row", np.int64), ("score", np.float32),
+                      ("camera", np.int32)], align=True)
+assert HIT_DTYPE.itemsize == 24
 
 
 def last_error() -> str:

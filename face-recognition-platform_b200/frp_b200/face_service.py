@@ -13,7 +13,7 @@ batch_compare_faces    face_service.py:448-481                   frp_match
 find_k_nearest         face_service.py:590-612                   frp_match (no thr.)
 store_face (dup scan)  face_service.py:344-390 (:352-364)        frp_match (strict)
 delete_face            face_service.py:517-547                   frp_gallery_remove
-cluster_faces          face_service.py:552-585                   frp_scores
+cluster_faces          face_service.py:552-585                   frp_cluster
 get_all_targets        face_service.py:511-512                   —
 match_topk (new)       routes/face.py:688-693 threshold + top-k  frp_match
 =====================  =======================================  ==================
@@ -36,7 +36,7 @@ from typing import Any, Callable, Dict, List, Optional
 import numpy as np
 
 from . import _capi
-from ._capi import (MATCH_NO_THRESHOLD, MATCH_STRICT, METRIC_COS, METRIC_L2, FrpError)
+from ._capi import (MATCH_NO_THRESHOLD, MATCH_STRICT, METRIC_COS, METRIC_L2, STATUS_UNCERTIFIED, FrpError)
 from .gallery import GalleryDict
 
 logger = logging.getLogger("frp_b200.face_service")
@@ -106,13 +106,16 @@ class FaceService:
                       return_distances: bool = True) -> List[Dict[str, Any]]:
         start_time = time.time()
         try:
-            names, rows = self._subset(target_names)
-            if not names:
-                logger.warning("No targets available for comparison")
-                return []
-            q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
-            all_v = self.encodings.gallery.scores(q)[0]
-            v = all_v[rows]
+            # one consistent view of (device gallery, row numbering): a concurrent compaction
+            # or clear waits until the scores are back (and vice versa)
+            with self.encodings.reading():
+                names, rows = self._subset(target_names)
+                if not names:
+                    logger.warning("No targets available for comparison")
+                    return []
+                q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
+                all_v = self.encodings.gallery.scores(q)[0]
+                v = all_v[rows]
             matches = self._is_match(v, self.tolerance)
             key = self._value_key()
             now = datetime.now().isoformat()
@@ -146,39 +149,51 @@ class FaceService:
     def batch_compare_faces(self, test_encodings: List[np.ndarray],
                             target_names: Optional[List[str]] = None) -> List[List[Dict[str, Any]]]:
         try:
-            names, rows = self._subset(target_names)
-            if not names:
-                return [[] for _ in test_encodings]
-            if len(test_encodings) == 0:
-                return []
-            Q = np.stack([np.asarray(t, dtype=np.float32).reshape(-1) for t in test_encodings])
-            key = self._value_key()
-            out: List[List[Dict[str, Any]]] = []
-            if target_names is None:
-                g = self.encodings.gallery
-                idx, sc, cnt, _ = g.match(Q, self.tolerance, MAX_NATIVE_K)
-                dense = None
-                for b in range(len(Q)):
-                    if cnt[b] >= MAX_NATIVE_K:      # possibly more matches than the native k cap
-                        if dense is None:
-                            dense = g.scores(Q)
-                        out.append(self._matches_from_dense(dense[b], names, rows))
-                        continue
-                    res = []
-                    for j in range(int(cnt[b])):
-                        val = float(sc[b, j])
-                        item = {"target": self.encodings.name_of(int(idx[b, j])), "match": True, key: val}
-                        if not self._cos:
-                            item["confidence"] = self._get_confidence_level(val)
-                        res.append(item)
-                    out.append(res)
-            else:
-                dense = self.encodings.gallery.scores(Q)
-                for b in range(len(Q)):
-                    out.append(self._matches_from_dense(dense[b], names, rows))
-            return out
+            with self.encodings.reading():
+                return self._batch_compare_locked(test_encodings, target_names)
         except Exception as e:
             return self._fail("batch_compare_faces", e, [[] for _ in test_encodings])
+
+    def _native_matches(self, Q: np.ndarray, tol: float, flags: int = 0):
+        """Threshold-then-top-64 on the device for every query (tcgen05 kernel for more than 4
+        queries).  Returns (idx, score, count, dense_needed[B]): a query needs the dense
+        all-scores path when its list is full (there may be more than 64 matches) or when the
+        native ladder could not certify it (status 2: more than 64 exact ties at the cut)."""
+        idx, sc, cnt, st = self.encodings.gallery.match(Q, tol, MAX_NATIVE_K, flags)
+        return idx, sc, cnt, (cnt >= MAX_NATIVE_K) | (st == STATUS_UNCERTIFIED)
+
+    def _batch_compare_locked(self, test_encodings, target_names):
+        names, rows = self._subset(target_names)
+        if not names:
+            return [[] for _ in test_encodings]
+        if len(test_encodings) == 0:
+            return []
+        Q = np.stack([np.asarray(t, dtype=np.float32).reshape(-1) for t in test_encodings])
+        key = self._value_key()
+        out: List[List[Dict[str, Any]]] = []
+        if target_names is None:
+            g = self.encodings.gallery
+            idx, sc, cnt, need_dense = self._native_matches(Q, self.tolerance)
+            dense = None
+            for b in range(len(Q)):
+                if need_dense[b]:
+                    if dense is None:
+                        dense = g.scores(Q)
+                    out.append(self._matches_from_dense(dense[b], names, rows))
+                    continue
+                res = []
+                for j in range(int(cnt[b])):
+                    val = float(sc[b, j])
+                    item = {"target": self.encodings.name_of(int(idx[b, j])), "match": True, key: val}
+                    if not self._cos:
+                        item["confidence"] = self._get_confidence_level(val)
+                    res.append(item)
+                out.append(res)
+        else:
+            dense = self.encodings.gallery.scores(Q)
+            for b in range(len(Q)):
+                out.append(self._matches_from_dense(dense[b], names, rows))
+        return out
 
     def _matches_from_dense(self, all_v, names, rows):
         key = self._value_key()
@@ -196,30 +211,36 @@ class FaceService:
 
     def find_k_nearest(self, test_encoding: np.ndarray, k: int = 5) -> List[Dict[str, Any]]:
         try:
-            if len(self.encodings) == 0:
-                return []
-            k = min(int(k), len(self.encodings))
-            q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
-            key = self._value_key()
-            g = self.encodings.gallery
-            if k <= MAX_NATIVE_K:
-                idx, sc, cnt, _ = g.match(q, 0.0, k, MATCH_NO_THRESHOLD)
-                pairs = [(int(idx[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
-            else:
-                v = g.scores(q)[0]
-                rows = self.encodings.live_rows()
-                order = np.argsort(-v[rows] if self._cos else v[rows], kind="stable")[:k]
-                pairs = [(int(rows[i]), float(v[rows[i]])) for i in order]
-            results = []
-            for row, val in pairs:
-                item = {"target": self.encodings.name_of(row), key: val}
-                if not self._cos:
-                    item["confidence"] = self._get_confidence_level(val)
-                    item["confidence_score"] = self._calibrate_confidence(val)
-                results.append(item)
-            return results
+            with self.encodings.reading():
+                return self._find_k_nearest_locked(test_encoding, k)
         except Exception as e:
             return self._fail("find_k_nearest", e, [])
+
+    def _find_k_nearest_locked(self, test_encoding, k):
+        if len(self.encodings) == 0:
+            return []
+        k = min(int(k), len(self.encodings))
+        q = np.asarray(test_encoding, dtype=np.float32).reshape(1, -1)
+        key = self._value_key()
+        g = self.encodings.gallery
+        pairs = None
+        if k <= MAX_NATIVE_K:
+            idx, sc, cnt, st = g.match(q, 0.0, k, MATCH_NO_THRESHOLD)
+            if st[0] != STATUS_UNCERTIFIED:
+                pairs = [(int(idx[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
+        if pairs is None:
+            v = g.scores(q)[0]
+            rows = self.encodings.live_rows()
+            order = np.argsort(-v[rows] if self._cos else v[rows], kind="stable")[:k]
+            pairs = [(int(rows[i]), float(v[rows[i]])) for i in order]
+        results = []
+        for row, val in pairs:
+            item = {"target": self.encodings.name_of(row), key: val}
+            if not self._cos:
+                item["confidence"] = self._get_confidence_level(val)
+                item["confidence_score"] = self._calibrate_confidence(val)
+            results.append(item)
+        return results
 
     def match_topk(self, queries, threshold: Optional[float] = None, top_k: int = 5,
                    thresholded: bool = True):
@@ -228,12 +249,28 @@ class FaceService:
         materialising N dicts.  Returns one list of (target, value) per query."""
         tol = self.tolerance if threshold is None else threshold
         Q = np.atleast_2d(np.asarray(queries, dtype=np.float32))
-        if len(self.encodings) == 0:
-            return [[] for _ in Q]
+        kk = min(int(top_k), MAX_NATIVE_K)
         flags = 0 if thresholded else MATCH_NO_THRESHOLD
-        idx, sc, cnt, _ = self.encodings.gallery.match(Q, tol, min(int(top_k), MAX_NATIVE_K), flags)
-        return [[(self.encodings.name_of(int(idx[b, j])), float(sc[b, j])) for j in range(int(cnt[b]))]
-                for b in range(len(Q))]
+        with self.encodings.reading():
+            enc = self.encodings
+            if len(enc) == 0:
+                return [[] for _ in Q]
+            g = enc.gallery
+            idx, sc, cnt, st = g.match(Q, tol, kk, flags)
+            out = []
+            dense = None
+            for b in range(len(Q)):
+                if st[b] == STATUS_UNCERTIFIED:     # > 64 exact ties at the cut: dense scores decide
+                    if dense is None:
+                        dense = g.scores(Q)
+                    rows = enc.live_rows()
+                    v = dense[b][rows]
+                    keep = np.nonzero(self._is_match(v, tol))[0] if thresholded else np.arange(len(rows))
+                    order = keep[np.argsort(-v[keep] if self._cos else v[keep], kind="stable")][:kk]
+                    out.append([(enc.name_of(int(rows[i])), float(v[i])) for i in order])
+                else:
+                    out.append([(enc.name_of(int(idx[b, j])), float(sc[b, j])) for j in range(int(cnt[b]))])
+            return out
 
     # ------------------------------------------------------------------ mutate
     def get_all_targets(self) -> List[str]:
@@ -247,18 +284,19 @@ class FaceService:
             if len(enc) and not self._cos:
                 # first existing face (dict order) closer than 0.3, self excluded (face_service.py:352-364)
                 q = np.asarray(encoding_list, dtype=np.float32).reshape(1, -1)
-                idx, sc, cnt, _ = enc.gallery.match(q, 0.3, MAX_NATIVE_K, MATCH_STRICT)
-                if cnt[0] >= MAX_NATIVE_K:
-                    v = enc.gallery.scores(q)[0]
-                    cand = [r for r in enc.live_rows() if v[r] < 0.3]
-                else:
-                    cand = sorted(int(i) for i in idx[0, :cnt[0]])
-                for r in cand:
-                    name = enc.name_of(int(r))
-                    if name is not None and name != target_name:
-                        is_duplicate, similar_target = True, name
-                        logger.warning("Potential duplicate: %s ~ %s", target_name, name)
-                        break
+                with enc.reading():
+                    idx, sc, cnt, need_dense = self._native_matches(q, 0.3, MATCH_STRICT)
+                    if need_dense[0]:
+                        v = enc.gallery.scores(q)[0]
+                        cand = [r for r in enc.live_rows() if v[r] < 0.3]
+                    else:
+                        cand = sorted(int(i) for i in idx[0, :cnt[0]])
+                    for r in cand:
+                        name = enc.name_of(int(r))
+                        if name is not None and name != target_name:
+                            is_duplicate, similar_target = True, name
+                            logger.warning("Potential duplicate: %s ~ %s", target_name, name)
+                            break
             already_exists = target_name in enc
             if self._persist is not None and not self._persist(target_name, encoding_list):
                 return {"success": False, "message": "Failed to store in database", "is_duplicate": is_duplicate}
@@ -294,29 +332,22 @@ class FaceService:
     def cluster_faces(self, distance_threshold: float = 0.6) -> Dict[str, List[str]]:
         """Greedy seed clustering of face_service.py:552-585: every not-yet-assigned
         face (dict order) seeds a cluster and absorbs all unassigned faces within
-        the threshold (inclusive)."""
-        enc = self.encodings
-        if len(enc) < 2:
-            return {"cluster_0": enc.keys()}
-        names = enc.keys()
-        rows = np.array([enc.row_of(t) for t in names], dtype=np.int64)
-        assigned = np.zeros(len(names), bool)
-        clusters: Dict[str, List[str]] = {}
-        cid = 0
-        g = enc.gallery
-        for i, target in enumerate(names):
-            if assigned[i]:
-                continue
-            assigned[i] = True
-            seed = g.get_row(int(rows[i]))[None, :]
-            v = g.scores(seed)[0][rows]
-            close = self._is_match(v, distance_threshold) & ~assigned
-            close[i] = False
-            members = [target] + [names[j] for j in np.nonzero(close)[0]]
-            assigned |= close
-            clusters["cluster_%d" % cid] = members
-            cid += 1
-        return clusters
+        the threshold (inclusive).  The gallery is matched against itself on the device
+        (frp_cluster: 256-row query slabs through the tcgen05 matcher, thresholded neighbour
+        lists only); a seed always precedes its members in dict order, so grouping the labels
+        in row order reproduces the reference's member order."""
+        try:
+            with self.encodings.reading():
+                enc = self.encodings
+                if len(enc) < 2:
+                    return {"cluster_0": enc.keys()}
+                labels, n, _ = enc.gallery.cluster(distance_threshold)
+                clusters: Dict[str, List[str]] = {"cluster_%d" % c: [] for c in range(n)}
+                for name, row in enc._rows.items():          # dict order == row order
+                    clusters["cluster_%d" % int(labels[row])].append(name)
+                return clusters
+        except Exception as e:
+            return self._fail("cluster_faces", e, {})
 
     # ----------------------------------------------------------------- metrics
     def get_performance_metrics(self) -> Dict[str, Any]:

@@ -18,7 +18,83 @@ from typing import Dict, Iterable, Iterator, List, Optional
 import numpy as np
 
 from . import _capi
-from ._capi import METRIC_COS, METRIC_L2, check, lib, ptr
+from ._capi import FRP_E_RANGE, METRIC_COS, METRIC_L2, FrpError, check, lib, ptr
+
+
+class RWLock:
+    """Readers-writer lock for the gallery bookkeeping: matchers (readers) hold it across
+    subset -> device call -> row->name translation, so a compaction or ``clear`` (writers) can
+    never swap the device gallery or renumber rows under them.  Writer-preferring; re-entrant
+    for the thread that already holds it (a writer may read, a reader may read again)."""
+
+    def __init__(self):
+        self._cond = threading.Condition(threading.Lock())
+        self._readers = 0
+        self._writer = None
+        self._wdepth = 0
+        self._waiting_writers = 0
+        self._local = threading.local()
+
+    def acquire_read(self):
+        me = threading.get_ident()
+        depth = getattr(self._local, "rdepth", 0)
+        with self._cond:
+            if self._writer == me or depth:
+                self._local.rdepth = depth + 1
+                return
+            while self._writer is not None or self._waiting_writers:
+                self._cond.wait()
+            self._readers += 1
+            self._local.rdepth = 1
+
+    def release_read(self):
+        me = threading.get_ident()
+        with self._cond:
+            self._local.rdepth -= 1
+            if self._local.rdepth or self._writer == me:
+                return
+            self._readers -= 1
+            if not self._readers:
+                self._cond.notify_all()
+
+    def acquire_write(self):
+        me = threading.get_ident()
+        with self._cond:
+            if self._writer == me:
+                self._wdepth += 1
+                return
+            if getattr(self._local, "rdepth", 0):
+                raise RuntimeError("cannot upgrade a gallery read lock to a write lock")
+            self._waiting_writers += 1
+            while self._writer is not None or self._readers:
+                self._cond.wait()
+            self._waiting_writers -= 1
+            self._writer = me
+            self._wdepth = 1
+
+    def release_write(self):
+        with self._cond:
+            self._wdepth -= 1
+            if not self._wdepth:
+                self._writer = None
+                self._cond.notify_all()
+
+    class _Ctx:
+        def __init__(self, acq, rel):
+            self._acq, self._rel = acq, rel
+
+        def __enter__(self):
+            self._acq()
+
+        def __exit__(self, *exc):
+            self._rel()
+            return False
+
+    def read(self):
+        return RWLock._Ctx(self.acquire_read, self.release_read)
+
+    def write(self):
+        return RWLock._Ctx(self.acquire_write, self.release_write)
 
 
 class Gallery:
@@ -92,6 +168,12 @@ class Gallery:
     def set_base(self, base_row: int) -> None:
         check(lib.frp_gallery_set_base(self.handle, int(base_row)))
 
+    def set_seq(self, first_row: int, seqs) -> None:
+        """Explicit global sequence numbers for rows [first_row, first_row + len(seqs))
+        (mutable row shards)."""
+        a = np.ascontiguousarray(np.asarray(seqs, dtype=np.uint64).reshape(-1))
+        check(lib.frp_gallery_set_seq(self.handle, int(first_row), len(a), ptr(a) if len(a) else None))
+
     # -- queries --------------------------------------------------------------
     def counts(self):
         rows, live = C.c_uint64(0), C.c_uint64(0)
@@ -146,15 +228,34 @@ class Gallery:
                                    stream or None))
 
     def scores(self, queries) -> np.ndarray:
-        """All scores [B, rows] in float64 from the fp32 master (NaN = deleted row)."""
+        """All scores [B, rows] in float64 from the fp32 master (NaN = deleted row).  The row
+        count is the one the native call observed under its lock (``rows_out``), never an
+        earlier read: a concurrent append cannot overrun the buffer (FRP_E_RANGE -> retry)."""
         q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
         if q.shape[1] != self.dim:
             raise ValueError("expected queries of length %d, got %d" % (self.dim, q.shape[1]))
+        for _ in range(8):
+            stride = self.rows + 64
+            out = np.empty((q.shape[0], stride), np.float64)
+            got = C.c_uint64(0)
+            rc = lib.frp_scores(self.handle, ptr(q), q.shape[0], ptr(out), stride, C.byref(got))
+            if rc == FRP_E_RANGE:
+                continue                      # the gallery grew past the slack between the two calls
+            check(rc)
+            return out[:, :got.value]
+        raise FrpError(FRP_E_RANGE, "gallery kept growing while frp_scores was sizing its output")
+
+    def cluster(self, tau: float, flags: int = 0):
+        """Greedy seed clustering on the device (frp_cluster).  Returns (labels[rows] int32 with
+        -1 for deleted rows, n_clusters, stats dict)."""
         rows = self.rows
-        out = np.empty((q.shape[0], rows), np.float64)
-        if rows:
-            check(lib.frp_scores(self.handle, ptr(q), q.shape[0], ptr(out)))
-        return out
+        labels = np.empty(rows + 64, np.int32)
+        n = C.c_int(0)
+        stats = np.zeros(4, np.uint64)
+        check(lib.frp_cluster(self.handle, float(tau), int(flags), ptr(labels), len(labels), C.byref(n), ptr(stats)))
+        rows_now = min(self.rows, len(labels))
+        return labels[:rows_now], int(n.value), {"slabs": int(stats[0]), "rows_matched": int(stats[1]),
+                                                  "dense_fallbacks": int(stats[2]), "kernel_launches": int(stats[3])}
 
 
 class GalleryDict:
@@ -171,7 +272,7 @@ class GalleryDict:
         self.device = device
         self.keep_host = keep_host
         self.compact_ratio = compact_ratio
-        self._lock = threading.RLock()
+        self._lock = RWLock()                    # readers: matchers; writers: every mutation
         self._rows: Dict[str, int] = {}          # name -> row; insertion order == row order
         self._names: List[Optional[str]] = []    # row -> name (None = tombstone)
         self._host: Dict[str, list] = {}
@@ -181,6 +282,12 @@ class GalleryDict:
     @property
     def gallery(self) -> Optional[Gallery]:
         return self._gallery
+
+    def reading(self):
+        """Context manager: a consistent view of (device gallery, row numbering, names) for the
+        duration of one match (subset -> native call -> ``name_of``).  Compaction, ``clear`` and
+        every other mutation wait for the readers and vice versa."""
+        return self._lock.read()
 
     def row_of(self, name: str) -> int:
         return self._rows[name]
@@ -205,13 +312,14 @@ class GalleryDict:
 
     def compact(self):
         """Drop tombstones; live rows keep their relative order."""
-        with self._lock:
+        with self._lock.write():
             if self._gallery is None or len(self._names) == len(self._rows):
                 return
             live = self.live_rows()
             new = self._gallery.gather(live)
-            self._gallery.close()
+            old = self._gallery
             self._gallery = new
+            old.close()          # no reader holds it: the write lock excludes them
             self._names = list(self._rows.keys())
             self._rows = {n: i for i, n in enumerate(self._names)}
 
@@ -219,7 +327,7 @@ class GalleryDict:
         """Append many (name, row) pairs at once (start-up load; the reference's
         retrieve_all_embeddings, utils/db.py:484-490, has no caller)."""
         a = np.asarray(rows)
-        with self._lock:
+        with self._lock.write():
             if len(set(names)) != len(names) or any(n in self._rows for n in names):
                 raise ValueError("bulk_load needs new, distinct names")
             g = self._ensure(a.shape[1])
@@ -234,7 +342,7 @@ class GalleryDict:
     # -- dict protocol ------------------------------------------------------
     def __setitem__(self, name: str, value) -> None:
         vec = np.asarray(value, dtype=np.float64).reshape(-1)
-        with self._lock:
+        with self._lock.write():
             g = self._ensure(vec.shape[0])
             if name in self._rows:
                 g.update(self._rows[name], vec)
@@ -247,14 +355,14 @@ class GalleryDict:
                 self._host[name] = value if isinstance(value, list) else vec.tolist()
 
     def __getitem__(self, name: str) -> list:
-        with self._lock:
+        with self._lock.read():
             row = self._rows[name]
             if self.keep_host:
                 return self._host[name]
             return self._gallery.get_row(row).astype(np.float64).tolist()
 
     def __delitem__(self, name: str) -> None:
-        with self._lock:
+        with self._lock.write():
             row = self._rows.pop(name)
             self._names[row] = None
             self._host.pop(name, None)
@@ -286,7 +394,7 @@ class GalleryDict:
         return self[name] if name in self._rows else default
 
     def pop(self, name, *default):
-        with self._lock:
+        with self._lock.write():
             if name not in self._rows:
                 if default:
                     return default[0]
@@ -296,7 +404,7 @@ class GalleryDict:
             return v
 
     def clear(self) -> None:
-        with self._lock:
+        with self._lock.write():
             if self._gallery is not None:
                 self._gallery.close()
             self._gallery = None

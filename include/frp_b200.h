@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRP_ABI_VERSION 1
+#define FRP_ABI_VERSION 2
 
 /* error codes */
 #define FRP_OK            0
@@ -59,6 +59,8 @@ extern "C" {
 /* per-query status written by frp_match */
 #define FRP_STATUS_OK        0  /* result certified exact w.r.t. the fp32 master */
 #define FRP_STATUS_FALLBACK  1  /* fp16 prefilter could not be certified; result came from the fp32 scan */
+#define FRP_STATUS_UNCERTIFIED 2 /* still uncertified after both fallbacks (> 64 exact ties at the cut):
+                                    the caller must use frp_scores for this query */
 
 typedef struct frp_gallery frp_gallery_t;   /* opaque; replaces state.ENCODINGS (state.py:78) */
 
@@ -102,11 +104,21 @@ int frp_gallery_info(const frp_gallery_t* g, int* device, int* dim, int* dimp, i
 int frp_gallery_gather(const frp_gallery_t* g, const uint64_t* idx, uint64_t n, frp_gallery_t** out);
 /* read back the fp32 master row (COS: normalised) */
 int frp_gallery_get_row(const frp_gallery_t* g, uint64_t row, float* out);
-/* flat binary snapshot: header + fp32 master rows + alive flags */
+/* flat binary snapshot: header + fp32 master rows + alive flags.  save writes
+ * `path + ".tmp"` and renames it over `path`; load validates the header against the file size
+ * and rebuilds the fp16 copy / norms / error bound from the stored master VERBATIM (no
+ * re-normalisation), so a loaded gallery answers bit-identically to the saved one. */
 int frp_gallery_save(const frp_gallery_t* g, const char* path);
 int frp_gallery_load(int device, const char* path, frp_gallery_t** out);
 /* global row index of local row 0 (row-sharded galleries); added to out_idx */
 int frp_gallery_set_base(frp_gallery_t* g, uint64_t base_row);
+/* Mutable row-sharded galleries ("appends to the least-full shard with global seq
+ * kept per row"): give rows [first_row, first_row + n) explicit global sequence numbers.  Once
+ * a gallery carries sequences, out_idx reports seq[row] instead of base_row + row, and the
+ * cross-shard merge breaks ties by it.  Sequences must increase with the local row (append in
+ * global insertion order), so the local tie order equals the global one.  Not persisted by
+ * frp_gallery_save (the sharded dict keeps them with its names). */
+int frp_gallery_set_seq(frp_gallery_t* g, uint64_t first_row, uint64_t n, const uint64_t* seq);
 
 /* ---- 1:N match: replaces face_distance + `<= tolerance` + sort + [:top_k]
  *      (face_service.py:410-411,431-432; routes/face.py:692-693) and the
@@ -123,20 +135,29 @@ int frp_match_device(frp_gallery_t* g, const float* queries_dev, int B, double t
                      int flags, int64_t* out_idx_dev, float* out_score_dev,
                      int32_t* out_count_dev, int32_t* out_status_dev, void* stream);
 /* all N scores of every query from the fp32 master in float64 (the O(N) dict
- * list compare_faces returns, face_service.py:414-429).  out [B][rows] host. */
-int frp_scores(frp_gallery_t* g, const float* queries, int B, double* out);
-int frp_scores_device(frp_gallery_t* g, const float* queries_dev, int B, double* out_dev, void* stream);
-/* Row-sharded galleries (one rank per GPU): every rank packs its
- * frp_match_device outputs into one record
- *     idx[B][k] i64 | score[B][k] f32 | count[B] i32 | status[B] i32   (padded to 16 B)
- * of frp_shard_record_bytes(B,k) bytes; ncclAllGather concatenates the R records;
- * frp_merge_packed_device merges them into the global top-k [B][k] (better score
- * first, ties by global row) and ORs the per-shard status words into
- * *out_any_status (may be NULL). */
+ * list compare_faces returns, face_service.py:414-429).  out [B][out_stride] (row b of the
+ * result starts at out + b * out_stride); the gallery's row count at the time of the call is
+ * returned in *rows_out (may be NULL) and must not exceed out_stride (FRP_E_RANGE otherwise,
+ * nothing written): the count is read and used under one lock, so a concurrent store_face
+ * can never make the call write past the caller's buffer.  NaN marks deleted rows. */
+int frp_scores(frp_gallery_t* g, const float* queries, int B, double* out, uint64_t out_stride,
+               uint64_t* rows_out);
+int frp_scores_device(frp_gallery_t* g, const float* queries_dev, int B, double* out_dev,
+                      uint64_t out_stride, uint64_t* rows_out, void* stream);
+/* Row-sharded galleries (one rank per GPU): frp_match_record_device runs the local match and
+ * writes ONE packed record straight into the caller's all-gather send buffer
+ *     idx[B][k] i64 | score[B][k] f64 | count[B] i32 | status[B] i32   (padded to 16 B)
+ * of frp_shard_record_bytes(B,k) bytes (scores travel in float64 so the cross-shard merge
+ * ranks exactly like the single-gallery re-rank); ncclAllGather concatenates the R records;
+ * frp_merge_packed_device merges them into the global top-k [B][k] (better score first, ties
+ * by global row = gallery base_row + local row) and ORs the per-shard status words into
+ * *out_any_status (may be NULL).  out_score64 (may be NULL) receives the float64 scores. */
 size_t frp_shard_record_bytes(int B, int k);
+int frp_match_record_device(frp_gallery_t* g, const float* queries_dev, int B, double tau, int k,
+                            int flags, void* record_dev, void* stream);
 int frp_merge_packed_device(int metric, int R, int B, int k, const void* records_dev,
-                            int64_t* out_idx, float* out_score, int32_t* out_count,
-                            int32_t* out_any_status, void* stream);
+                            int64_t* out_idx, float* out_score, double* out_score64,
+                            int32_t* out_count, int32_t* out_any_status, void* stream);
 
 /* Fused exchange + merge over peer memory (NVLink/NVSwitch), replacing the all-gather:
  * every rank owns an exchange buffer of frp_exchange_buffer_bytes(R,B,k) bytes that is
@@ -151,6 +172,50 @@ int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void*
                           void* const* peers_dev, uint32_t epoch, unsigned int* counter_dev,
                           int64_t* out_idx, float* out_score, int32_t* out_count,
                           int32_t* out_any_status, void* stream);
+
+/* ---- gallery against itself: cluster_faces (face_service.py:552-585) -------------------
+ * Greedy seed clustering on the device gallery: rows in insertion order; an unassigned live
+ * row seeds a cluster and absorbs every unassigned live row within tau (inclusive `<=` / `>=`,
+ * strict with FRP_MATCH_STRICT).  The gallery is matched against itself in slabs of up to 256
+ * seed candidates through the same prefilter + exact re-rank as frp_match (tcgen05 kernel);
+ * only the thresholded neighbour lists come back to the host, which runs the greedy pass.
+ * labels [rows] receives the cluster id of every row (ids number the seeds in order; -1 for
+ * deleted rows), *n_clusters the number of clusters.  stats (may be NULL) receives
+ * {slabs, rows matched on the device, rows that needed the dense fallback, kernel launches}. */
+int frp_cluster(frp_gallery_t* g, double tau, int flags, int32_t* labels, uint64_t labels_len,
+                int32_t* n_clusters, uint64_t* stats4);
+
+/* ---- match -> tracking hand-off: cooldown table on the device ---------
+ * tracking_service.record_detection drops a (person, camera) detection that arrives within
+ * `cooldown` seconds of the last RECORDED one (tracking_service.py:118-134, :179).  The table
+ * is an open-addressing hash in HBM keyed by (global gallery row, camera id); the filter runs
+ * on the match results while they are still on the device, so cooled-down hits are never
+ * copied back or turned into Python objects. */
+typedef struct frp_cooldown frp_cooldown_t;
+/* capacity = number of (row, camera) slots (rounded up to a power of two, >= 1024) */
+int frp_cooldown_create(int device, uint64_t capacity, frp_cooldown_t** out);
+int frp_cooldown_destroy(frp_cooldown_t* c);
+int frp_cooldown_clear(frp_cooldown_t* c, void* stream);
+/* Inputs (device): idx [B][k] / score [B][k] / count [B] as written by frp_match_device;
+ * camera [B] i32 = camera id of each query; limit [B] f32 (may be NULL) = per-query second
+ * filter `distance <= limit` (`similarity >= limit` for metric COS), routes/camera.py:250.
+ * A hit (b, j) is RECORDED when it passes the limit and its (row, camera) key was last
+ * recorded more than `cooldown` seconds before `now` (or never); within one call the first
+ * hit in (b, j) order wins a key, like the reference's sequential loop.  Outputs (device):
+ * hits [B*k] records {int32 b, int32 j, int64 idx, float score, int32 camera} compacted in
+ * (b, j) order, *n_hits.  A full table drops nothing: the hit is recorded and bit 0 of
+ * *overflow is set. */
+typedef struct frp_hit { int32_t query; int32_t rank; int64_t row; float score; int32_t camera; } frp_hit_t;
+int frp_cooldown_filter_device(frp_cooldown_t* c, int metric, const int64_t* idx_dev,
+                               const float* score_dev, const int32_t* count_dev,
+                               const int32_t* camera_dev, const float* limit_dev, int B, int k,
+                               double now, double cooldown, frp_hit_t* hits_dev, int32_t* n_hits_dev,
+                               int32_t* overflow_dev, void* stream);
+/* host-buffer convenience: match + filter in one call, only the recorded hits come back.
+ * hits [B*k]; returns the number of hits in *n_hits. */
+int frp_match_hits(frp_gallery_t* g, frp_cooldown_t* c, const float* queries, int B, double tau, int k,
+                   int flags, const int32_t* camera, const float* limit, double now, double cooldown,
+                   frp_hit_t* hits, int32_t* n_hits);
 
 /* ---- alignment: insightface face_align.norm_crop + blobFromImages
  *      (third-party; only call site backend/app/utils/deepfake_utils.py:138) -- */

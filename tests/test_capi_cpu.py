@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version_and_record_size():
-    assert _capi.lib.frp_abi_version() == 1
+    assert _capi.lib.frp_abi_version() == 2
     for B, k in ((1, 1), (3, 10), (256, 10), (1024, 64)):
         assert _capi.lib.frp_shard_record_bytes(B, k) == record_bytes(B, k)
 
@@ -185,8 +185,8 @@ def test_record_pack_roundtrip():
     for r in range(R):
         rec = buf[r * nb:(r + 1) * nb]
         rec[:B * k * 8].view(np.int64)[:] = np.arange(B * k) + 100 * r
-        rec[B * k * 8:B * k * 12].view(np.float32)[:] = np.arange(B * k) * 0.5 + r
-        rec[B * k * 12:B * k * 12 + B * 4].view(np.int32)[:] = r + 1
+        rec[B * k * 8:B * k * 16].view(np.float64)[:] = np.arange(B * k) * 0.5 + r
+        rec[B * k * 16:B * k * 16 + B * 4].view(np.int32)[:] = r + 1
     idx, sc, cnt, st = unpack_records(buf, R, B, k)
     assert idx.shape == (R, B, k) and idx[1, 0, 0] == 100 and sc[1, 0, 1] == 1.5 and cnt[1, 2] == 2
 

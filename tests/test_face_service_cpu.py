@@ -57,6 +57,21 @@ class _NumpyGallery:
         out[:, ~np.array(self.alive)] = np.nan
         return out
 
+    def cluster(self, tau, flags=0):
+        """Contract of frp_cluster: greedy seed labels in row order, -1 for deleted rows."""
+        G = np.stack(self.data)
+        alive = np.array(self.alive)
+        labels = np.full(len(G), -1, np.int32)
+        cid = 0
+        for i in range(len(G)):
+            if not alive[i] or labels[i] >= 0:
+                continue
+            d = np.linalg.norm(G - G[i], axis=1)
+            labels[alive & (labels < 0) & (d <= tau)] = cid
+            labels[i] = cid
+            cid += 1
+        return labels, cid, {}
+
     def match(self, queries, tau, k, flags=0):
         S = self.scores(queries)
         B = S.shape[0]
