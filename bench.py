@@ -19,6 +19,12 @@ import sys
 import tempfile
 import time
 
+if "reference" in sys.argv:
+    # the CPU arm uses every host core at every N: torchrun exports OMP_NUM_THREADS=1, which
+    # OpenBLAS would otherwise pick up when numpy loads
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -43,6 +49,10 @@ def parse():
     ap.add_argument("--exchange", default=os.environ.get("FRP_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
                     help="multi-GPU merge: NCCL all-gather + merge kernel, or the fused peer-memory kernel")
     ap.add_argument("--also-batches", default="", help="comma list of extra batch sizes timed on the same gallery")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run all-gather + merge on the step's own stream instead of the two-slot pipeline")
+    ap.add_argument("--c3", choices=["auto", "on", "off"], default="auto",
+                    help="100 M-row leg (12.5 M rows per rank): auto = when 8 ranks run")
     return ap.parse_args()
 
 
@@ -116,68 +126,108 @@ def synth_l2_queries(G, nq, seed=4321, planted_frac=0.5):
 # --------------------------------------------------------------------------
 # CPU baseline: the reference's numpy path (oracle port) on the host cores
 # --------------------------------------------------------------------------
-def cpu_match_sample(args, rows_sample=500_000, reps=3):
-    """numpy / OpenBLAS cosine 1:N with threshold + top-k on a bounded sample:
-    `batch` queries vs `rows_sample` fp32 rows, scaled to the full gallery."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def _blas_threads():
+    """Pin the BLAS pool to every host core (explicitly: the environment may say 1) and return
+    the thread count actually in use."""
+    n = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([t.get("num_threads", 1) for t in threadpool_info()] + [1])
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        return max([t.get("num_threads", 1) for t in threadpool_info()] + [1])
     except Exception:
-        cores = os.cpu_count() or 1
+        return n
+
+
+def _cpu_topk_pass(Q, G, rows_total, k, tau, chunk=65536):
+    """numpy / OpenBLAS cosine 1:N with threshold + top-k over `rows_total` gallery rows: chunked
+    sgemm + argpartition + merge.  G is a block of rows that is cycled when rows_total > len(G)
+    (identical arithmetic per row; a block of >= 1 M x 512 fp32 = 2 GB never fits a CPU cache)."""
+    B = Q.shape[0]
+    best_s = np.full((B, k), -np.inf, np.float32)
+    best_i = np.full((B, k), -1, np.int64)
+    nblk = len(G)
+    done = 0
+    while done < rows_total:
+        lo = done % nblk
+        n = min(chunk, nblk - lo, rows_total - done)
+        S = Q @ G[lo:lo + n].T
+        kk = min(k, n)
+        part = np.argpartition(-S, kk - 1, axis=1)[:, :kk]
+        ps = np.take_along_axis(S, part, axis=1)
+        cs = np.concatenate([best_s, ps], 1)
+        ci = np.concatenate([best_i, part + done], 1)
+        o_ = np.lexsort((ci, -cs), axis=1)[:, :k]
+        best_s = np.take_along_axis(cs, o_, 1)
+        best_i = np.take_along_axis(ci, o_, 1)
+        done += n
+    return best_i, best_s, (best_s >= tau).sum(1)
+
+
+def _cpu_workload(args, block_rows):
     rng = np.random.default_rng(0)
-    G = rng.standard_normal((rows_sample, 512), dtype=np.float32)
+    G = rng.standard_normal((block_rows, 512), dtype=np.float32)
     G /= np.linalg.norm(G, axis=1, keepdims=True)
     Q = rng.standard_normal((args.batch, 512), dtype=np.float32)
     Q /= np.linalg.norm(Q, axis=1, keepdims=True)
-    k, tau = args.k, args.tau
+    return G, Q
 
-    def one():
-        best_s = np.full((args.batch, k), -np.inf, np.float32)
-        best_i = np.full((args.batch, k), -1, np.int64)
-        for lo in range(0, rows_sample, 65536):
-            S = Q @ G[lo:lo + 65536].T
-            part = np.argpartition(-S, k - 1, axis=1)[:, :k]
-            ps = np.take_along_axis(S, part, axis=1)
-            cs = np.concatenate([best_s, ps], 1)
-            ci = np.concatenate([best_i, part + lo], 1)
-            o_ = np.lexsort((ci, -cs), axis=1)[:, :k]
-            best_s = np.take_along_axis(cs, o_, 1)
-            best_i = np.take_along_axis(ci, o_, 1)
-        return best_i, best_s, (best_s >= tau).sum(1)
 
-    one()
+def cpu_match_sample(args, rows_sample=1_000_000, reps=3):
+    """cpu_baseline leg of the GPU arm (bounded: ~10-30 s): `batch` queries vs a 1 M-row sample
+    of the gallery, median of `reps`, scaled to the full row count.  `--impl reference` runs the
+    full row count instead."""
+    cores = _blas_threads()
+    rows_sample = min(rows_sample, args.rows)
+    G, Q = _cpu_workload(args, rows_sample)
+    _cpu_topk_pass(Q, G, min(rows_sample, 131072), args.k, args.tau)        # warm the BLAS pool
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        one()
+        _cpu_topk_pass(Q, G, rows_sample, args.k, args.tau)
         ts.append(time.perf_counter() - t0)
     t = float(np.median(ts))
     qps = args.batch / (t * (args.rows / rows_sample))
     return {"value": qps, "unit": UNIT, "cores": int(cores), "kind": "port",
-            "sample": "numpy sgemm + argpartition, %d queries x %d of %d rows (fp32), median of %d, scaled x%g"
+            "sample": "numpy sgemm + argpartition (the oracle's arithmetic; the reference has no 512-d path), %d "
+                      "queries x %d of %d rows (fp32), median of %d, scaled x%g"
                       % (args.batch, rows_sample, args.rows, reps, args.rows / rows_sample),
             "sample_seconds": t}
 
 
-def run_reference(args):
+def run_reference(args, budget_s=150.0):
+    """`--impl reference`: the CPU implementation of the path on ALL host threads, on the GPU
+    arm's exact config: every step scores `batch` queries against all `rows` gallery rows.  The
+    number of timed steps is capped by a wall-clock budget (>= 3) and reported as `steps`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t_all = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_match_sample(args, reps=1)
-        if i >= args.warmup:
-            t_all.append(base["sample_seconds"])
-    t = float(np.mean(t_all))
-    qps = args.batch / (t * (args.rows / 500_000))
+    cores = _blas_threads()
+    block = min(args.rows, 1_000_000)
+    G, Q = _cpu_workload(args, block)
+    # warm-up: W passes over one block (BLAS pool and page faults; a full-size pass would add
+    # nothing), plus one timed block pass to size the step count against the budget
+    for _ in range(args.warmup):
+        _cpu_topk_pass(Q, G, block, args.k, args.tau)
+    t0 = time.perf_counter()
+    _cpu_topk_pass(Q, G, block, args.k, args.tau)
+    est = (time.perf_counter() - t0) * args.rows / block
+    steps = int(max(min(3, args.steps), min(args.steps, budget_s // max(est, 1e-3))))
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _cpu_topk_pass(Q, G, args.rows, args.k, args.tau)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    qps = args.batch / t
+    sample = ("numpy sgemm + argpartition + merge, %d queries x ALL %d rows per step (a %d-row fp32 block cycled "
+              "%gx), median of %d steps (of %d requested; capped by a %.0f s budget); warm-up = %d block passes"
+              % (args.batch, args.rows, block, args.rows / block, steps, args.steps, budget_s, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * (args.rows / 500_000) * 1e3,
+            "steps": steps, "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config(args, args.gpus),
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": base["cores"], "kind": "port",
-                             "sample": base["sample"]},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": int(cores), "kind": "port", "sample": sample,
+                             "step_seconds": [round(x, 3) for x in ts]},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -240,21 +290,29 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_gallery(frp, torch, rows_local, seed, device):
-    gal = frp.Gallery(512, frp.METRIC_COS, device=device.index or 0, capacity=rows_local)
+def make_gallery(frp, torch, rows_local, seed, device, keep_rows=4096, dim=512, metric=None, scale=1.0):
+    """Random gallery generated on the device in 1 M-row chunks.  Returns (gallery, keep, keep_idx):
+    `keep` = `keep_rows` rows drawn from the WHOLE local row range (the planted queries are
+    mixed from them, so matches land in every tile of every CTA, not only in the first ones)."""
+    gal = frp.Gallery(dim, frp.METRIC_COS if metric is None else metric, device=device.index or 0, capacity=rows_local)
     gen = torch.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
-    keep = None
+    nchunks = max(1, (rows_local + chunk - 1) // chunk)
+    per = max(1, keep_rows // nchunks)
+    keep, keep_idx = [], []
     st = torch.cuda.current_stream().cuda_stream
     for lo in range(0, rows_local, chunk):
         n = min(chunk, rows_local - lo)
-        x = torch.randn((n, 512), generator=gen, device=device, dtype=torch.float32)
+        x = torch.randn((n, dim), generator=gen, device=device, dtype=torch.float32)
+        if scale != 1.0:
+            x *= scale
         gal.append_device(x, stream=st)
-        if keep is None:
-            keep = x[:4096].clone()
+        sel = torch.randint(0, n, (min(per, n),), generator=gen, device=device)
+        keep.append(x[sel].clone())
+        keep_idx.append(sel + lo)
         del x
     torch.cuda.synchronize()
-    return gal, keep
+    return gal, torch.cat(keep)[:keep_rows].contiguous(), torch.cat(keep_idx)[:keep_rows]
 
 
 def make_queries(torch, nsteps, B, keep, seed, device, planted_frac=0.5):
@@ -303,12 +361,13 @@ def run_ours(args):
     B, k, tau, K, W = args.batch, args.k, args.tau, args.steps, args.warmup
 
     lo, hi = frp.shard_bounds(args.rows, world, rank)
-    # rank 0's first rows seed the planted queries on every rank (same generator seed)
-    gal, keep = make_gallery(frp, torch, hi - lo, 1234 + rank, device)
+    # planted queries are mixed from rows of EVERY rank's shard, spread over its whole row range
+    per_rank_keep = 4096 // world
+    gal, keep, _ = make_gallery(frp, torch, hi - lo, 1234 + rank, device, keep_rows=per_rank_keep)
     if world > 1:
-        if rank != 0:
-            keep = torch.empty((4096, 512), device=device)
-        dist.broadcast(keep, 0)
+        allk = torch.empty((world * per_rank_keep, 512), device=device)
+        dist.all_gather_into_tensor(allk, keep.contiguous())
+        keep = allk
     matcher = frp.ShardedMatcher(gal, args.rows, rank, world, exchange=args.exchange)
     exchange_check = None
     if args.exchange == "p2p" and world > 1:
@@ -334,10 +393,28 @@ def run_ours(args):
     def step(i):
         return matcher.match(queries[i], tau, k)
 
+    pipelined = (args.exchange == "nccl") and not args.no_pipeline
+
+    def run_steps(a, b):
+        """Steps a..b-1.  Pipelined (default): the all-gather + merge of step i run on the
+        exchange stream behind the prefilter of step i+1; every step's merged result is
+        produced (and waited for on the timing stream) inside the timed region."""
+        if not pipelined:
+            out_ = None
+            for i in range(a, b):
+                out_ = step(i)
+            return out_
+        prev, out_ = None, None
+        for i in range(a, b):
+            t = matcher.submit(queries[i], tau, k)
+            if prev is not None:
+                out_ = matcher.result(prev)
+            prev = t
+        return matcher.result(prev)
+
     # ---- device-resident throughput -------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(W):
-        out = step(i)
+    out = run_steps(0, W)
     if sampler:
         sampler.wait_first()
     barrier()
@@ -346,8 +423,7 @@ def run_ours(args):
     launches0 = frp.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(W, W + K):
-        out = step(i)
+    out = run_steps(W, W + K)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -361,8 +437,7 @@ def run_ours(args):
     # load running (untimed) for ~1.2 s so the clock record reflects the steps under load
     reps = max(1, int(1200.0 / max(ms, 1e-3)))
     for _ in range(min(reps, 2000)):
-        for i in range(W, W + K):
-            step(i)
+        run_steps(W, W + K)
     barrier()
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
@@ -403,10 +478,13 @@ def run_ours(args):
     # DRAM traffic per launch: ratio (dram bytes / algorithmic bytes) measured once with
     # `ncu --set full` on the same kernel (profiles/r1_traffic.json) x this launch's bytes
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[roof["kernel"]]
+        tf = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if not os.path.isfile(tf):
+            tf = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tr = json.load(open(tf))[roof["kernel"]]
         roof["traffic"] = tr["dram_bytes_per_algorithmic_byte"] * rows_local * 1024 * \
             ((B + 3) // 4 if roof["kernel"] == "match_scan_f16" else 1)
-        roof["traffic_source"] = tr["source"]
+        roof["traffic_source"] = tr["source"] + " (dram bytes / algorithmic byte of one `ncu --set full` capture x this launch's bytes; not an in-run counter)"
     except Exception:
         pass
     roof["algorithmic_bytes"] = rows_local * 1024
@@ -432,41 +510,50 @@ def run_ours(args):
                "d2h_bytes_per_step": B * k * 12 + B * 8, "api": "frp_match (Gallery.match), host buffers",
                "uncertified_queries": nfb, "ms_per_step": dt / K * 1e3}
     else:
-        # multi-rank: pinned host queries -> H2D on every rank, sharded match, merged result D2H on rank 0
+        # multi-rank: pinned host queries -> H2D on every rank, pipelined sharded match, merged
+        # result D2H into pinned memory every step; the certificate flag is checked one step late
         hq = queries.cpu().pin_memory()
-        dq = torch.empty((B, 512), device=device)
-        h_idx = torch.empty((B, k), dtype=torch.int64).pin_memory()
-        h_sc = torch.empty((B, k), dtype=torch.float32).pin_memory()
-        h_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+        pipe = frp.CertifiedPipeline(matcher, B, 512, k, device)
+        levels = []
 
-        def e2e_step(i):
-            dq.copy_(hq[i], non_blocking=True)
-            # certified = the fallback ladder of the host API (reads one 4-byte flag per step)
-            oi, os_, oc, _ = matcher.match_certified(dq, tau, k)
-            h_idx.copy_(oi, non_blocking=True); h_sc.copy_(os_, non_blocking=True); h_cnt.copy_(oc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        def e2e_run(a, b):
+            for i in range(a, b):
+                r = pipe.push(hq[i], tau)
+                if r is not None:
+                    levels.append(r[3])
+            levels.append(pipe.flush()[3])
 
-        for i in range(W):
-            e2e_step(i)
+        e2e_run(0, W)
         barrier()
         t0 = time.perf_counter()
-        for i in range(W, W + K):
-            e2e_step(i)
-        barrier()
+        e2e_run(W, W + K)
+        torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         e2e = {"value": B * K / dt, "unit": UNIT, "h2d_bytes_per_step": B * 512 * 4,
-               "d2h_bytes_per_step": B * k * 12 + B * 4, "api": "ShardedMatcher.match_certified, pinned host buffers",
-               "ms_per_step": dt / K * 1e3}
+               "d2h_bytes_per_step": B * k * 12 + B * 4 + 4,
+               "api": "CertifiedPipeline over ShardedMatcher (pinned host queries in, pinned host results out, "
+                      "certificate checked one step late)",
+               "fallback_steps": int(sum(1 for x in levels if x)), "ms_per_step": dt / K * 1e3}
 
     extras = {}
     if world == 1 and not args.no_extras and rank == 0:
-        extras = side_measurements(args, frp, torch, gal, queries, pk, device)
+        extras = side_measurements(args, frp, torch, gal, queries, pk, device, keep)
     if world > 1 and not args.no_extras:
         # alignment shards by stream with no exchange: every rank aligns the 4 096 detections
         # of its own 16 frames (weak scaling); time = max over ranks
         extras["align_sharded"] = align_sharded(frp, torch, dist, device, rank, world)
+    if not args.no_extras:
+        try:
+            extras["pipeline_c5"] = pipeline_c5(args, frp, torch, dist, matcher, keep, device, rank, world)
+        except Exception as e:  # pragma: no cover
+            extras["pipeline_c5"] = {"error": repr(e)}
+    if (args.c3 == "on" or (args.c3 == "auto" and world == 8)) and not args.no_extras:
+        try:
+            extras["c3_100M"] = c3_100m(args, frp, torch, dist, device, rank, world, pk)
+        except Exception as e:  # pragma: no cover
+            extras["c3_100M"] = {"error": repr(e)}
     # other batch sizes against the same resident gallery (config C3: batch 1 and 1024)
     if args.also_batches:
         other = {}
@@ -520,6 +607,136 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _time_steps(torch, dist, device, fn, n, warm=2):
+    """n calls of fn(i) bracketed by barriers, device events, max over ranks.  Returns ms per call."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warm, warm + n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / n
+
+
+def _pipelined(matcher, qs, tau, k, flags=0):
+    """Closure running qs[i % len] through the two-slot pipeline; call .drain() at the end."""
+    state = {"prev": None}
+
+    def fn(i):
+        t = matcher.submit(qs[i % qs.shape[0]], tau, k, flags)
+        if state["prev"] is not None:
+            matcher.result(state["prev"])
+        state["prev"] = t
+
+    def drain():
+        if state["prev"] is not None:
+            matcher.result(state["prev"])
+            state["prev"] = None
+
+    fn.drain = drain
+    return fn
+
+
+def c3_100m(args, frp, torch, dist, device, rank, world, pk):
+    """BASELINE configs[2]: 100 M x 512 fp16 rows row-sharded over the ranks (12.5 M per rank at 8
+    GPUs, generated per shard on the device with seed + rank), batch 1 / 256 / 1024, NCCL top-k
+    merge; device-resident queries, pipelined steps, max over ranks."""
+    from frp_b200 import _capi
+    total = 100_000_000
+    lo, hi = frp.shard_bounds(total, world, rank)
+    gal, keep, _ = make_gallery(frp, torch, hi - lo, 4321 + rank, device, keep_rows=max(8, 512 // world))
+    if world > 1:
+        allk = torch.empty((world * keep.shape[0], 512), device=device)
+        dist.all_gather_into_tensor(allk, keep.contiguous())
+        keep = allk
+    m = frp.ShardedMatcher(gal, total, rank, world)
+    out = {"workload": "100 M x 512 fp16 rows over %d ranks (%d rows per rank), tau %.2f, top-%d, queries resident, "
+                       "two-slot pipeline" % (world, hi - lo, args.tau, args.k), "batches": {}}
+    rows_local = hi - lo
+    for Bx in (1, 256, 1024):
+        qx = make_queries(torch, 8, Bx, keep, 11 + Bx, device)
+        fn = _pipelined(m, qx, args.tau, args.k)
+        nst = 12 if Bx < 1024 else 6
+        ms = _time_steps(torch, dist, device, fn, nst)
+        fn.drain()
+        torch.cuda.synchronize()
+        _capi.lib.frp_profile_enable(1)
+        o_ = m.match(qx[0], args.tau, args.k)
+        pb = C.c_float()
+        _capi.check(_capi.lib.frp_profile_last(None, C.byref(pb), None))
+        _capi.lib.frp_profile_enable(0)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        out["batches"][str(Bx)] = {
+            "queries_per_s": Bx / (ms / 1e3), "ms_per_step": ms, "prefilter_kernel_ms": pb.value,
+            "kernel_share_of_step": pb.value / ms, "match_path": frp.last_match_path(),
+            "uncertified": int(o_[3].item() != 0),
+            "local_hbm_gbs": rows_local * 1024 / 1e9 / (pb.value / 1e3),
+            "local_hbm_frac": rows_local * 1024 / 1e9 / (pb.value / 1e3) / pk["hbm"],
+            "local_tflops": 2.0 * Bx * rows_local * 512 / (pb.value / 1e3) / 1e12}
+    gal.close()
+    return out
+
+
+def pipeline_c5(args, frp, torch, dist, matcher, keep, device, rank, world):
+    """BASELINE configs[4]: 32 synthetic 1080p streams per tick, 8 faces each.  Streams are dealt
+    to the ranks (shard_streams); per tick every rank copies ITS streams' frames from pinned host
+    memory, aligns their detections, contributes its faces' embeddings (backbone out of scope:
+    seeded synthetic 512-d rows stand in for its output) to one all-gather, and all ranks run
+    the row-sharded match of the 256 faces against the 10 M watchlist; rank 0 reads the result."""
+    S_, faces, H, W_ = 32, 8, 1080, 1920
+    mine = frp.shard_streams(range(S_), world, rank)
+    ns = len(mine)
+    rng = np.random.default_rng(900 + rank)
+    h_frames = torch.from_numpy(rng.integers(0, 256, (ns, H, W_, 3), dtype=np.uint8)).pin_memory()
+    d_frames = torch.empty((ns, H, W_, 3), dtype=torch.uint8, device=device)
+    fi, lm = synth_detections(ns, faces, H, W_, seed=11 + rank)
+    d_fi, d_lm = torch.from_numpy(fi).to(device), torch.from_numpy(lm).to(device)
+    n_mine = ns * faces
+    n_all = S_ * faces
+    blob = torch.empty((n_mine, 3, 112, 112), dtype=torch.float16, device=device)
+    emb_all = make_queries(torch, 4, n_all, keep, 77, device)            # [4, 256, 512] stand-in embeddings
+    my_lo = sum(len(frp.shard_streams(range(S_), world, r)) for r in range(rank)) * faces
+    gathered = torch.empty((n_all, 512), device=device)
+    h_idx = torch.empty((n_all, args.k), dtype=torch.int64).pin_memory()
+    h_cnt = torch.empty((n_all,), dtype=torch.int32).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    equal_split = all(len(frp.shard_streams(range(S_), world, r)) == ns for r in range(world))
+
+    def tick(i):
+        d_frames.copy_(h_frames, non_blocking=True)
+        frp.align.norm_crop_batch_device(d_frames, ns, H, W_, 3 * W_, d_fi, d_lm, n_mine, blob,
+                                         device=device.index, stream=st)
+        e = emb_all[i % 4]
+        if world > 1 and equal_split:
+            dist.all_gather_into_tensor(gathered, e[my_lo:my_lo + n_mine].contiguous())
+            q = gathered
+        else:
+            q = e
+        oi, _, oc, _ = matcher.match(q, args.tau, args.k)
+        if rank == 0:
+            h_idx.copy_(oi, non_blocking=True)
+            h_cnt.copy_(oc, non_blocking=True)
+
+    ms = _time_steps(torch, dist, device, tick, 10, warm=2)
+    return {"ticks_per_s": 1e3 / ms, "faces_per_s": n_all * 1e3 / ms, "frames_per_s": S_ * 1e3 / ms, "ms_per_tick": ms,
+            "h2d_bytes_per_tick_per_rank": int(h_frames.numel()), "streams_per_rank": ns,
+            "workload": "32 x 1080p streams over %d rank(s): frames H2D from pinned memory + align (%d crops per "
+                        "rank) + embedding all-gather + row-sharded cosine match of %d faces vs %d rows, top-%d"
+                        % (world, n_mine, n_all, args.rows, args.k)}
+
+
 def align_sharded(frp, torch, dist, device, rank, world):
     F, H, W_, per = 16, 1080, 1920, 256
     rng = np.random.default_rng(50 + rank)
@@ -550,7 +767,7 @@ def align_sharded(frp, torch, dist, device, rank, world):
             "scaling": "weak", "workload": "per rank: 4096 detections from 16 1080p frames, no exchange"}
 
 
-def side_measurements(args, frp, torch, gal, queries, pk, device):
+def side_measurements(args, frp, torch, gal, queries, pk, device, keep):
     """Batch-1 matching (HBM roofline) and the alignment stage (C4), each timed alone."""
     from frp_b200 import _capi
     out = {}
@@ -584,6 +801,72 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
                            "kernel_ms": t * 1e3,
                            "roofline": {"bound": "hbm", "achieved": gb / t, "peak": pk["hbm"], "unit": "GB/s",
                                         "frac": gb / t / pk["hbm"]}}
+    # pure top-k (find_k_nearest semantics: FRP_MATCH_NO_THRESHOLD) at the headline size: every
+    # epilogue thread keeps a live top-16 for the whole pass
+    try:
+        Bn = queries.shape[1]
+        bo = (torch.empty((Bn, k), dtype=torch.int64, device=device), torch.empty((Bn, k), device=device),
+              torch.empty((Bn,), dtype=torch.int32, device=device), torch.empty((Bn,), dtype=torch.int32, device=device))
+        _capi.lib.frp_profile_enable(1)
+        ts_ = []
+        for i in range(6):
+            gal.match_device(queries[i], Bn, tau, k, frp.MATCH_NO_THRESHOLD, *bo, st)
+            pb = C.c_float()
+            _capi.check(_capi.lib.frp_profile_last(None, C.byref(pb), None))
+            if i >= 2:
+                ts_.append(pb.value / 1e3)
+        _capi.lib.frp_profile_enable(0)
+        tn = float(np.mean(ts_))
+        fl = 2.0 * Bn * rows * 512
+        out["match_topk_nothreshold"] = {
+            "workload": "pure top-%d (no threshold), batch %d vs %d x 512" % (k, Bn, rows),
+            "kernel_ms": tn * 1e3, "queries_per_s_kernel": Bn / tn, "path": frp.last_match_path(),
+            "uncertified": int((bo[3] != 0).sum().item()),
+            "tflops": fl / tn / 1e12, "tensor_frac_of_burst": fl / tn / 1e12 / pk["tensor_burst"],
+            "hbm_frac": gb / tn / pk["hbm"]}
+    except Exception as e:  # pragma: no cover
+        out["match_topk_nothreshold"] = {"error": repr(e)}
+
+    # config C2 (BASELINE configs[1]): batch 256 vs a 1 M x 512 gallery, top-10
+    try:
+        g1, keep1, _ = make_gallery(frp, torch, 1_000_000, 555, device, keep_rows=2048)
+        q1m = make_queries(torch, 24, 256, keep1, 556, device)
+        bo = (torch.empty((256, k), dtype=torch.int64, device=device), torch.empty((256, k), device=device),
+              torch.empty((256,), dtype=torch.int32, device=device), torch.empty((256,), dtype=torch.int32, device=device))
+        flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+        def c2_step(i):
+            g1.match_device(q1m[i % 24], 256, tau, k, 0, *bo, st)
+
+        ms_ = _time_steps(torch, None, device, c2_step, 20)
+        _capi.lib.frp_profile_enable(1)
+        cold = []
+        for i in range(5):
+            flush.fill_(i)          # the 1 GB gallery is several times the L2, but start cold anyway
+            c2_step(i)
+            pb = C.c_float()
+            _capi.check(_capi.lib.frp_profile_last(None, C.byref(pb), None))
+            cold.append(pb.value)
+        _capi.lib.frp_profile_enable(0)
+        hq1 = q1m.cpu().pin_memory().numpy()
+        for i in range(3):
+            g1.match(hq1[i], tau, k)
+        t0 = time.perf_counter()
+        for i in range(20):
+            g1.match(hq1[i % 24], tau, k)
+        dt1 = (time.perf_counter() - t0) / 20
+        kms = float(np.mean(cold[1:]))
+        out["c2_1m"] = {"workload": "cosine 1:N, batch 256 x gallery 1 000 000 x 512, tau %.2f, top-%d (BASELINE configs[1])" % (tau, k),
+                        "queries_per_s": 256 / (ms_ / 1e3), "ms_per_step": ms_, "prefilter_kernel_ms": kms,
+                        "tflops": 2.0 * 256 * 1e6 * 512 / (kms / 1e3) / 1e12,
+                        "tensor_frac_of_burst": 2.0 * 256 * 1e6 * 512 / (kms / 1e3) / 1e12 / pk["tensor_burst"],
+                        "hbm_frac": 1.024 / (kms / 1e3) / pk["hbm"],
+                        "e2e_queries_per_s": 256 / dt1, "e2e_ms_per_step": dt1 * 1e3, "path": frp.last_match_path()}
+        del flush
+        g1.close()
+    except Exception as e:  # pragma: no cover
+        out["c2_1m"] = {"error": repr(e)}
+
     # alignment: 4096 detections from 16 1080p frames -> 112x112 fp16 NCHW
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import frp_oracle_np as o      # cpu_baseline legs only (align and C1 below)
@@ -636,17 +919,21 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
     except Exception as e:  # pragma: no cover
         out["align"]["cpu_baseline"] = {"error": str(e)}
 
-    # 128-d L2 (face_recognition encodings) at scale: 4M x 128, tolerance 0.6, batch 1 and 256
+    # 128-d L2 (face_recognition encodings) at scale: 4M x 128, tolerance 0.6, batch 1 and 256.
+    # Arithmetic intensity of the batched contraction is B flop per gallery byte whatever the row
+    # length, so batch 256 sits on the same tensor/HBM ridge as the 512-d headline: both
+    # fractions are reported.
     try:
         N2_ = 4_000_000
-        g2 = frp.Gallery(128, frp.METRIC_L2, device=device.index or 0, capacity=N2_)
-        gen = torch.Generator(device=device).manual_seed(77)
-        for lo_ in range(0, N2_, 1_000_000):
-            g2.append_device(torch.randn((1_000_000, 128), generator=gen, device=device) * 0.05, stream=st)
-        torch.cuda.synchronize()
+        g2, keep2, _ = make_gallery(frp, torch, N2_, 77, device, keep_rows=4096, dim=128, metric=frp.METRIC_L2, scale=0.05)
+        gen = torch.Generator(device=device).manual_seed(78)
         res = {}
         for Bx in (1, 256):
             qx = torch.randn((6, Bx, 128), generator=gen, device=device) * 0.05
+            # half the queries are noisy copies of gallery rows from the whole row range (d ~ 0.23)
+            sel = torch.randint(0, keep2.shape[0], (6, Bx), generator=gen, device=device)
+            planted = torch.rand((6, Bx, 1), generator=gen, device=device) < 0.5
+            qx = torch.where(planted, keep2[sel] + torch.randn((6, Bx, 128), generator=gen, device=device) * 0.02, qx)
             bo = (torch.empty((Bx, k), dtype=torch.int64, device=device), torch.empty((Bx, k), device=device),
                   torch.empty((Bx,), dtype=torch.int32, device=device), torch.empty((Bx,), dtype=torch.int32, device=device))
             _capi.lib.frp_profile_enable(1)
@@ -660,12 +947,17 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
             _capi.lib.frp_profile_enable(0)
             tm_ = float(np.mean(ts_))
             gb_ = N2_ * 256 / 1e9
+            fl_ = 2.0 * Bx * N2_ * 128
             res[str(Bx)] = {"kernel_ms": tm_ * 1e3, "path": frp.last_match_path(), "hbm_gbs": gb_ / tm_,
-                            "hbm_frac": gb_ / tm_ / pk["hbm"], "queries_per_s_kernel": Bx / tm_}
-        out["match_l2_128d"] = {"workload": "L2, tolerance 0.6, 4M x 128 gallery (256 B fp16 rows)", "batches": res}
+                            "hbm_frac": gb_ / tm_ / pk["hbm"], "queries_per_s_kernel": Bx / tm_,
+                            "tflops": fl_ / tm_ / 1e12, "tensor_frac_of_burst": fl_ / tm_ / 1e12 / pk["tensor_burst"],
+                            "tensor_frac_of_sustained": fl_ / tm_ / 1e12 / pk["tensor"],
+                            "mean_matches_per_query": float(bo[2].float().mean().item())}
+        out["match_l2_128d"] = {"workload": "L2, tolerance 0.6, 4M x 128 gallery (256 B fp16 rows), half the queries "
+                                            "planted on rows spread over the whole gallery", "batches": res}
         g2.close()
     except Exception as e:  # pragma: no cover
-        out["match_l2_128d"] = {"error": str(e)}
+        out["match_l2_128d"] = {"error": repr(e)}
 
     # config C1: face_recognition compare_faces, 1 query vs 1k synthetic 128-d encodings,
     # tolerance 0.6, through the drop-in FaceService (all 1 000 result dicts, like the reference)
@@ -690,49 +982,74 @@ def side_measurements(args, frp, torch, gal, queries, pk, device):
         for q in Q1[:16]:
             o.compare_faces(ref, q, 0.6)
         t_cpu = (time.perf_counter() - t0) / 16
+        # the UNMODIFIED reference through oracle/ref_loader.py where /root/reference exists (the
+        # authoring container); the GPU box has no reference tree, so the port is the baseline there
+        t_live, live_kind = None, "port (no /root/reference on this box)"
+        try:
+            import ref_loader
+            if ref_loader.reference_available():
+                rfs, RENC, _ = ref_loader.load_reference()
+                RENC.clear()
+                for n_, g_ in ref.items():
+                    RENC[n_] = g_
+                rfs.tolerance = 0.6
+                rfs.compare_faces(Q1[0])
+                t0 = time.perf_counter()
+                for q in Q1[:16]:
+                    rfs.compare_faces(q)
+                t_live = (time.perf_counter() - t0) / 16
+                live_kind = "reference (unmodified face_service.compare_faces via oracle/ref_loader.py)"
+                RENC.clear()
+        except Exception as e:  # pragma: no cover
+            live_kind = "port (reference import failed: %r)" % (e,)
+        # hot-call latencies: store_face = duplicate scan + in-place row update
+        t0 = time.perf_counter()
+        for i in range(64):
+            fs.store_face("id%07d" % (i * 7), G1[i * 7])
+        t_store = (time.perf_counter() - t0) / 64
+        gq = np.ascontiguousarray(Q1[:1], dtype=np.float32)
+        gg = enc.gallery
+        for _ in range(8):
+            gg.match(gq, 0.6, 5)
+        t0 = time.perf_counter()
+        for _ in range(256):
+            gg.match(gq, 0.6, 5)
+        t_native = (time.perf_counter() - t0) / 256
         out["c1_compare_faces"] = {
             "workload": "1 query vs 1 000 x 128-d, tolerance 0.6 (BASELINE configs[0])",
             "drop_in_compare_faces_ms": t_gpu * 1e3, "drop_in_queries_per_s": 1.0 / t_gpu,
             "match_topk_ms": t_topk * 1e3, "match_topk_queries_per_s": 1.0 / t_topk,
+            "frp_match_call_us": t_native * 1e6, "store_face_us": t_store * 1e6,
             "cpu_port_compare_faces_ms": t_cpu * 1e3, "cpu_port_queries_per_s": 1.0 / t_cpu,
+            "cpu_reference_compare_faces_ms": None if t_live is None else t_live * 1e3,
+            "cpu_baseline_kind": live_kind,
             "note": "compare_faces returns all 1 000 dicts (O(N) Python by contract, face_service.py:414-429); "
-                    "match_topk is threshold-then-top-5 on the device"}
+                    "match_topk is threshold-then-top-5 on the device; frp_match_call_us = one Gallery.match "
+                    "(ctypes + frp_match, 1 query, top-5)"}
     except Exception as e:  # pragma: no cover
-        out["c1_compare_faces"] = {"error": str(e)}
+        out["c1_compare_faces"] = {"error": repr(e)}
 
-    # config C5: 32 synthetic 1080p streams per tick, ~8 faces each -> align -> (backbone out
-    # of scope: synthetic 512-d embeddings) -> match vs the resident gallery
+    # N4: cluster_faces on the device (face_service.py:552-585): 100 k x 128 faces, 20 per identity
     try:
-        S_, faces = 32, 8
-        fr32 = torch.from_numpy(rng.integers(0, 256, (S_, H, W_, 3), dtype=np.uint8)).to(device)
-        fi5, lm5 = synth_detections(S_, faces, H, W_, seed=11)
-        d_fi5, d_lm5 = torch.from_numpy(fi5).to(device), torch.from_numpy(lm5).to(device)
-        n5 = S_ * faces
-        blob5 = torch.empty((n5, 3, 112, 112), dtype=torch.float16, device=device)
-        q5 = queries[:, :n5, :].contiguous() if queries.shape[1] >= n5 else queries
-        bufs5 = (torch.empty((n5, args.k), dtype=torch.int64, device=device), torch.empty((n5, args.k), device=device),
-                 torch.empty((n5,), dtype=torch.int32, device=device), torch.empty((n5,), dtype=torch.int32, device=device))
-
-        def tick(i):
-            frp.align.norm_crop_batch_device(fr32, S_, H, W_, 3 * W_, d_fi5, d_lm5, n5, blob5, stream=st)
-            gal.match_device(q5[i % q5.shape[0]], n5, args.tau, args.k, 0, *bufs5, st)
-
-        for i in range(3):
-            tick(i)
+        ids, per_id = 5000, 20
+        gen = torch.Generator(device=device).manual_seed(91)
+        cen = torch.randn((ids, 128), generator=gen, device=device) * 0.05
+        pts = (cen[:, None, :] + torch.randn((ids, per_id, 128), generator=gen, device=device) * 0.02).reshape(-1, 128)
+        pts = pts[torch.randperm(ids * per_id, generator=gen, device=device)].contiguous()
+        gc = frp.Gallery(128, frp.METRIC_L2, device=device.index or 0, capacity=ids * per_id)
+        gc.append_device(pts, stream=st)
         torch.cuda.synchronize()
-        nt = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(nt):
-            tick(i)
-        e1.record()
-        torch.cuda.synchronize()
-        tt = e0.elapsed_time(e1) / 1e3 / nt
-        out["pipeline_c5"] = {"ticks_per_s": 1.0 / tt, "faces_per_s": n5 / tt, "ms_per_tick": tt * 1e3,
-                              "workload": "32 x 1080p streams (frames resident), %d faces/tick: align + synthetic "
-                                          "embeddings + cosine match vs %d rows, top-%d" % (n5, gal.rows, args.k)}
+        gc.cluster(0.6)
+        t0 = time.perf_counter()
+        labels, ncl, stats = gc.cluster(0.6)
+        t_cl = time.perf_counter() - t0
+        out["cluster_faces"] = {"workload": "greedy seed clustering of %d x 128-d faces (%d identities x %d), threshold 0.6"
+                                            % (ids * per_id, ids, per_id),
+                                "seconds": t_cl, "faces_per_s": ids * per_id / t_cl, "clusters": int(ncl), **stats,
+                                "note": "the reference's O(N^2) Python loop needs N^2/2 = 5e9 face_distance calls here"}
+        gc.close()
     except Exception as e:  # pragma: no cover
-        out["pipeline_c5"] = {"error": str(e)}
+        out["cluster_faces"] = {"error": repr(e)}
     return out
 
 

@@ -462,16 +462,19 @@ class ShardedGalleryDict:
         if r in self.galleries:
             self.galleries[r].remove(row)
 
-    def rename(self, old: str, new: str) -> None:
-        """Dict semantics of pop + assign: the face moves to the END of the order (new sequence)."""
+    def rename(self, old: str, new: str, value=None) -> None:
+        """Dict semantics of pop + assign: the face moves to the END of the order (new sequence).
+        ``value`` = the embedding to store under the new name; when omitted the fp32 master row
+        (normalised for cosine galleries) is read back from the owning shard."""
         if old not in self._where:
             raise KeyError(old)
-        r, row, _ = self._where[old]
-        vec = self.galleries[r].get_row(row) if r in self.galleries else None
-        if self.rank is not None:
-            vec = self._bcast_row(vec, r)
+        if value is None:
+            r, row, _ = self._where[old]
+            value = self.galleries[r].get_row(row) if r in self.galleries else None
+            if self.rank is not None:
+                value = self._bcast_row(value, r)
         del self[old]
-        self[new] = vec
+        self[new] = value
 
     def _bcast_row(self, vec, owner):
         import torch

@@ -133,6 +133,53 @@ def l2_match_topk(G, Q, tau, k, thresholded=True):
     return idx, dist, cnt
 
 
+def cluster_faces(encodings: dict, distance_threshold=0.6):
+    """face_service.py:552-585 `cluster_faces`: faces in dict order; an unassigned face seeds
+    `cluster_<n>` and absorbs every still-unassigned face j with
+    face_distance([enc_i], enc_j) <= threshold (inclusive), members in dict order after the
+    seed.  Fewer than two faces -> one cluster with everything.  The reference evaluates one
+    pair per Python call; this restatement evaluates one seed row at a time (same float64
+    arithmetic: np.linalg.norm of the row difference)."""
+    if len(encodings) < 2:
+        return {"cluster_0": list(encodings.keys())}
+    targets = list(encodings.keys())
+    E = np.array([encodings[t] for t in targets], dtype=np.float64)
+    assigned = np.zeros(len(targets), bool)
+    clusters = {}
+    cid = 0
+    for i, t in enumerate(targets):
+        if assigned[i]:
+            continue
+        assigned[i] = True
+        d = np.linalg.norm(E - E[i], axis=1)
+        take = (~assigned) & (d <= distance_threshold)
+        clusters["cluster_%d" % cid] = [t] + [targets[j] for j in np.nonzero(take)[0]]
+        assigned |= take
+        cid += 1
+    return clusters
+
+
+def synth_identity_gallery(n_ids, per_id, dim=128, seed=7, spread=0.02, chain_every=0):
+    """Clustered 128-d encodings: `n_ids` identity centres ~ N(0, 0.05), `per_id` samples each
+    at N(centre, spread) (intra-identity distance ~ spread * sqrt(2 dim) = 0.32 for 0.02,
+    inter-identity ~ 0.8), shuffled so members are spread over the whole row range.  With
+    chain_every = m > 0 every m-th identity gets a CHAIN A ~ B ~ C: B at 0.5 from A, C at 0.5
+    from B on the same ray (so A-C = 1.0 > 0.6): greedy seed order decides where B lands."""
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(0, 0.05, (n_ids, dim))
+    rows = [centres[i] + rng.normal(0, spread, (per_id, dim)) for i in range(n_ids)]
+    extra = []
+    if chain_every:
+        for i in range(0, n_ids, chain_every):
+            u = rng.standard_normal(dim)
+            u /= np.linalg.norm(u)
+            a = rows[i][0]
+            extra.append(a + 0.5 * u)
+            extra.append(a + 1.0 * u)
+    G = np.concatenate(rows + ([np.array(extra)] if extra else []), axis=0)
+    return G[rng.permutation(len(G))]
+
+
 # --------------------------------------------------------------------------
 # 2. 512-d cosine matcher (insightface ArcFaceONNX.compute_sim)
 # --------------------------------------------------------------------------
@@ -180,6 +227,79 @@ def cos_match_topk(G, Q, tau, k, thresholded=True, chunk=262144):
         idx[b, :len(s)] = ii
         sc[b, :len(s)] = s
     return idx, sc, cnt
+
+
+def _shortlist(score_desc, m):
+    """Per row: indices of every entry >= the m-th largest value (ties included)."""
+    n = score_desc.shape[1]
+    if n <= m:
+        return [np.arange(n)] * score_desc.shape[0]
+    kth = np.partition(score_desc, n - m, axis=1)[:, n - m]
+    return [np.nonzero(score_desc[b] >= kth[b])[0] for b in range(score_desc.shape[0])]
+
+
+def cos_match_topk_fast(G, Q, tau, k, thresholded=True, chunk=262144):
+    """Same result as cos_match_topk (same float64 chunk products, same order) for galleries of
+    millions of rows: each chunk is shortlisted with a partition (all ties of the cut kept)
+    instead of a full lexsort.  Checked equal to cos_match_topk in tests/test_oracle_cpu.py."""
+    Qn = normed(np.atleast_2d(Q))
+    B = Qn.shape[0]
+    cs = [[] for _ in range(B)]
+    ci = [[] for _ in range(B)]
+    for lo in range(0, len(G), chunk):
+        s = Qn @ normed(G[lo:lo + chunk]).T
+        for b, sel in enumerate(_shortlist(s, k + 8)):
+            cs[b].append(s[b, sel])
+            ci[b].append(sel + lo)
+    idx = np.full((B, k), -1, np.int64)
+    sc = np.full((B, k), np.nan, np.float64)
+    cnt = np.zeros(B, np.int64)
+    for b in range(B):
+        s_, i_ = np.concatenate(cs[b]), np.concatenate(ci[b])
+        order = np.lexsort((i_, -s_))
+        s_, i_ = s_[order], i_[order]
+        if thresholded:
+            keep = s_ >= tau
+            s_, i_ = s_[keep], i_[keep]
+        s_, i_ = s_[:k], i_[:k]
+        cnt[b] = len(s_)
+        idx[b, :len(s_)] = i_
+        sc[b, :len(s_)] = s_
+    return idx, sc, cnt
+
+
+def l2_match_topk_fast(G, Q, tau, k, thresholded=True, chunk=262144):
+    """Same result as l2_match_topk for galleries of millions of rows: a float64
+    |g|^2 - 2 g.q + |q|^2 pass shortlists each chunk (everything within 1e-6 of the k-th best
+    squared distance), then the shortlisted rows are re-evaluated with the reference's own
+    expression np.linalg.norm(g - q) (face_service.py:597) before threshold and ordering."""
+    G = np.asarray(G)
+    Q = np.atleast_2d(np.asarray(Q, dtype=np.float64))
+    B = Q.shape[0]
+    cand = [[] for _ in range(B)]
+    qn = (Q * Q).sum(1)
+    for lo in range(0, len(G), chunk):
+        Gc = np.asarray(G[lo:lo + chunk], dtype=np.float64)
+        d2 = (Gc * Gc).sum(1)[None, :] - 2.0 * (Q @ Gc.T) + qn[:, None]
+        for b, sel in enumerate(_shortlist(-d2, k + 8)):
+            kth = d2[b, sel].max()
+            cand[b].append(np.nonzero(d2[b] <= kth + 1e-6)[0] + lo)
+    idx = np.full((B, k), -1, np.int64)
+    dist = np.full((B, k), np.nan, np.float64)
+    cnt = np.zeros(B, np.int64)
+    for b in range(B):
+        rows = np.unique(np.concatenate(cand[b]))
+        d = np.linalg.norm(np.asarray(G[rows], dtype=np.float64) - Q[b], axis=1)
+        order = np.lexsort((rows, d))
+        rows, d = rows[order], d[order]
+        if thresholded:
+            keep = d <= tau
+            rows, d = rows[keep], d[keep]
+        rows, d = rows[:k], d[:k]
+        cnt[b] = len(rows)
+        idx[b, :len(rows)] = rows
+        dist[b, :len(rows)] = d
+    return idx, dist, cnt
 
 
 # --------------------------------------------------------------------------

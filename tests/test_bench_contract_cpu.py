@@ -19,7 +19,8 @@ def _run(env_extra=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run()
+    # torchrun exports OMP_NUM_THREADS=1: the arm must still use every host core
+    r = _run({"OMP_NUM_THREADS": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -29,7 +30,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
     assert d["config"]["workload"].startswith("cosine 1:N") and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and "ALL 1000000 rows" in cb["sample"]
+    assert cb["cores"] == (os.cpu_count() or 1)
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -137,11 +137,22 @@ def test_service_methods_match_reference_golden(golden_l2):
     assert np.abs(np.array([r["distance"] for r in res]) - g["sub_dist"]).max() < TIGHT
     assert fs.compare_faces(g["Q"][0], ["nope"]) == []
     # threshold + top-k like /face/compare (routes/face.py:685-693)
-    tk = fs.match_topk(g["Q"][:4], threshold=0.6, top_k=5)
-    for b in range(4):
+    tk = fs.match_topk(g["Q"], threshold=0.6, top_k=5)
+    for b in range(len(tk)):
         want = g["order"][b][g["match"][b]][:5].tolist()
-        assert [names.index(t) for t, _ in tk[b]] == want or True
-        assert len(tk[b]) == len(want)
+        got = [names.index(t) for t, _ in tk[b]]
+        if got != want:
+            # the only admissible difference: rows planted within 1e-6 of the tolerance, where the
+            # fp32 master and the reference's float64 lists may decide differently (gate: 1e-3)
+            sym = sorted(set(got) ^ set(want))
+            d = np.linalg.norm(g["G"][sym] - g["Q"][b], axis=1)
+            assert len(sym) and np.all(np.abs(d - 0.6) < 2e-6), (b, got, want)
+            common = [r for r in got if r in want]
+            assert common == [r for r in want if r in got]          # same order on the rows both hold
+        dd = np.array([v for _, v in tk[b]])
+        assert np.all(np.diff(dd) >= 0) and np.all(dd <= 0.6 + 2e-6)
+        ref_d = np.linalg.norm(g["G"][got] - g["Q"][b], axis=1)
+        assert np.abs(dd - ref_d).max(initial=0) < TIGHT
 
 
 def test_store_delete_mirror_dict_semantics():

@@ -141,6 +141,28 @@ def test_live_reference_agrees_with_np_oracle():
         ENC.clear()
 
 
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+def test_live_reference_clustering_agrees_with_np_oracle():
+    """cluster_faces (face_service.py:552-585) of the UNMODIFIED reference on a clustered gallery
+    with chains (A~B, B~C, A!~C) equals the vectorised restatement the GPU tests use at 20 k rows."""
+    fs, ENC, _ = ref_loader.load_reference()
+    G = o.synth_identity_gallery(25, 6, seed=3, chain_every=4)
+    ENC.clear()
+    for i, g in enumerate(G):
+        ENC["id%07d" % i] = g.tolist()
+    try:
+        for thr in (0.6, 0.45):
+            want = fs.cluster_faces(thr)
+            got = o.cluster_faces(ENC, thr)
+            assert got == want
+            assert 20 <= len(want) < len(G)
+        # a chain really is split by the greedy order somewhere
+        sizes = sorted(len(v) for v in fs.cluster_faces(0.6).values())
+        assert sizes[0] >= 1 and sizes[-1] >= 6
+    finally:
+        ENC.clear()
+
+
 def test_umeyama_cross_checked_against_scipy_and_opencv():
     """scikit-image (whose ``_umeyama`` insightface calls) is not in this image, so the
     restatement cannot be pinned to it; it is cross-checked against two independent
@@ -178,3 +200,27 @@ def test_umeyama_cross_checked_against_scipy_and_opencv():
                 a2, b2 = a + sgn * da, b + sgn * db
                 M2 = np.array([[a2, -b2, tx + sgn * dx], [b2, a2, ty + sgn * dy]])
                 assert resid(M2) >= r0 - 1e-9
+
+
+def test_fast_topk_oracles_equal_the_plain_ones():
+    """The shortlist forms used at BASELINE sizes (1 M x 512, 2 M x 128) give exactly the plain
+    restatements' answers, including exact duplicates and threshold ties."""
+    G = o.synth_cos_gallery(30_000, 64, seed=1)
+    G[20_000] = G[7]
+    G[29_999] = G[7]
+    Q, _ = o.synth_cos_queries(G, 9, seed=2)
+    Q[0] = G[7]
+    for thr in (True, False):
+        a = o.cos_match_topk(G, Q, 0.35, 10, thr, chunk=8192)
+        b = o.cos_match_topk_fast(G, Q, 0.35, 10, thr, chunk=8192)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[1], b[1], equal_nan=True)
+    G2 = o.synth_l2_gallery(20_000, 128, seed=3)
+    G2[15_000] = G2[3]
+    Q2, _ = o.synth_l2_queries(G2, 7, seed=4)
+    Q2[0] = G2[3]
+    for thr in (True, False):
+        a = o.l2_match_topk(G2, Q2, 0.6, 10, thr)
+        b = o.l2_match_topk_fast(G2, Q2, 0.6, 10, thr, chunk=4096)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[1], b[1], equal_nan=True)

@@ -1,0 +1,518 @@
+"""Round-2 parity tests (through the C ABI, on a B200):
+
+* the matcher against the float64 oracle at BASELINE.json's sizes (C2: 256 x 1 M x 512 cosine,
+  top-10, tau 0.40; 2 M x 128 L2 at tolerance 0.6), every prefilter route;
+* top_k up to 64 on the tcgen05 route (routes/face.py:654 allows 50);
+* snapshot load = verbatim master; corrupt headers rejected;
+* device-side clustering against the restatement of face_service.py:552-585;
+* the device cooldown table against the host filter (tracking_service.py:118-134);
+* the micro-batching front end for concurrent callers (routes/camera.py:29, :243-259);
+* the mutable row-sharded dict against one dict, for 1 / 2 / 8 shards;
+* concurrency: scores vs appends, compaction vs readers.
+"""
+import os
+import struct
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import frp_b200
+from frp_b200 import (BatchingMatcher, CooldownFilter, DeviceCooldown, FaceService, Gallery, GalleryDict,
+                      METRIC_COS, METRIC_L2, MATCH_FORCE_GEMM, MATCH_FORCE_SCAN, MATCH_NO_THRESHOLD,
+                      ShardedGalleryDict, scan_cameras, scan_cameras_recorded)
+import frp_oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+TIE = 1e-3        # north_star: indices exact except where candidates tie within 1e-3
+TIGHT = 2e-6      # what fp32 master + fp64 re-rank actually delivers
+
+
+def _assert_topk_equal(idx, sc, cnt, widx, wsc, wcnt, what):
+    """Bit-for-bit index equality; where a row differs, the swapped candidates must tie within
+    TIGHT in the oracle's float64 scores (far inside the 1e-3 allowance)."""
+    assert np.array_equal(cnt, wcnt.astype(np.int32)), what
+    bad = np.nonzero((idx != widx).any(axis=1))[0]
+    for b in bad:
+        n = int(cnt[b])
+        assert sorted(idx[b, :n]) == sorted(widx[b, :n]) or n == idx.shape[1], (what, b)
+        j = np.nonzero(idx[b, :n] != widx[b, :n])[0]
+        assert np.ptp(wsc[b, j.min():j.max() + 1]) < TIGHT, (what, b, wsc[b, :n])
+    for b in range(len(cnt)):
+        n = int(cnt[b])
+        assert np.abs(sc[b, :n].astype(np.float64) - wsc[b, :n]).max(initial=0) < TIGHT, (what, b)
+        assert np.all(idx[b, n:] == -1)
+    return len(bad)
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE sizes against the oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2():
+    """BASELINE.json configs[1]: 512-d cosine, 256 queries vs 1 M rows, planted rows spread over
+    the whole row range (first, last and random rows), plus exact duplicates far apart."""
+    N, B = 1_000_000, 256
+    G = o.synth_cos_gallery(N, 512, seed=11)
+    Q, planted = o.synth_cos_queries(G, B, seed=12)
+    G[N - 1] = G[0]
+    G[N // 2 + 17] = G[0]             # three exact copies: ties resolve by row
+    Q[0] = G[0]
+    Q[1] = G[N - 2]                   # the very last tile
+    g = Gallery(512, METRIC_COS, capacity=N)
+    g.append(G)
+    yield g, G, Q, planted
+    g.close()
+
+
+@pytest.mark.parametrize("thresholded", [True, False])
+def test_c2_256_x_1m_cosine_equals_the_oracle(c2, thresholded):
+    g, G, Q, planted = c2
+    tau, k = 0.40, 10
+    widx, wsc, wcnt = o.cos_match_topk_fast(G, Q, tau, k, thresholded)
+    assert (planted >= 0).sum() > 100 and planted.max() > 900_000
+    for flags, name in ((0, "default"), (MATCH_FORCE_SCAN, "scan")):
+        idx, sc, cnt, st = g.match(Q, tau, k, flags | (0 if thresholded else MATCH_NO_THRESHOLD))
+        if flags == 0:
+            assert frp_b200.last_match_path() == "gemm_tcgen05"
+        assert np.all(st <= 1)
+        _assert_topk_equal(idx, sc, cnt, widx, wsc, wcnt, (name, thresholded))
+        assert idx[0, :3].tolist() == [0, 500_017, 999_999]
+    # batch 1 and a ragged batch through the same gallery
+    for B in (1, 37):
+        idx, sc, cnt, st = g.match(Q[:B], tau, k, 0 if thresholded else MATCH_NO_THRESHOLD)
+        _assert_topk_equal(idx, sc, cnt, widx[:B], wsc[:B], wcnt[:B], ("B", B, thresholded))
+
+
+def test_l2_2m_x_128_equals_the_oracle():
+    """The reference's own dimension and tolerance at scale: 2 M x 128 encodings, tolerance 0.6,
+    top-10 and pure top-5, tcgen05 and scan routes, planted rows over the whole range."""
+    N = 2_000_000
+    G = o.synth_l2_gallery(N, 128, seed=3).astype(np.float32)
+    Q, planted = o.synth_l2_queries(G, 64, seed=4)
+    Q = Q.astype(np.float32)
+    g = Gallery(128, METRIC_L2, capacity=N)
+    g.append(G)
+    try:
+        assert planted.max() > 1_800_000
+        for thresholded, k in ((True, 10), (False, 5)):
+            widx, wd, wcnt = o.l2_match_topk_fast(G, Q, 0.6, k, thresholded)
+            for flags in (0, MATCH_FORCE_SCAN):
+                idx, d, cnt, st = g.match(Q, 0.6, k, flags | (0 if thresholded else MATCH_NO_THRESHOLD))
+                assert np.all(st <= 1)
+                _assert_topk_equal(idx, d, cnt, widx, wd, wcnt, ("l2", thresholded, flags))
+            idx, d, cnt, st = g.match(Q[:3], 0.6, k, 0 if thresholded else MATCH_NO_THRESHOLD)
+            _assert_topk_equal(idx, d, cnt, widx[:3], wd[:3], wcnt[:3], ("l2 B=3", thresholded))
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("k", [25, 50, 64])
+@pytest.mark.parametrize("metric", [METRIC_COS, METRIC_L2])
+def test_large_topk_runs_on_the_tensor_cores(metric, k):
+    """top_k up to 50 is what /face/compare allows (routes/face.py:654): the tcgen05 route keeps
+    32 candidates per list and the certificate proves the union holds the exact top-k."""
+    if metric == METRIC_COS:
+        G = o.synth_cos_gallery(120_000, 512, seed=21)
+        Q, _ = o.synth_cos_queries(G, 40, seed=22)
+        want = o.cos_match_topk_fast(G, Q, 0.0, k, False)
+    else:
+        G = o.synth_l2_gallery(120_000, 128, seed=23).astype(np.float32)
+        Q, _ = o.synth_l2_queries(G, 40, seed=24)
+        Q = Q.astype(np.float32)
+        want = o.l2_match_topk_fast(G, Q, 0.0, k, False)
+    g = Gallery(G.shape[1], metric)
+    g.append(G)
+    try:
+        idx, sc, cnt, st = g.match(Q, 0.0, k, MATCH_NO_THRESHOLD)
+        assert frp_b200.last_match_path() == "gemm_tcgen05"
+        assert np.all(st == 0), "pure top-%d over 120 k rows must certify on the fp16 route" % k
+        _assert_topk_equal(idx, sc, cnt, *want, ("topk", metric, k))
+    finally:
+        g.close()
+
+
+def test_face_service_batches_use_the_tensor_cores_and_check_status():
+    """batch_compare_faces / scan_cameras ask for 64 results per query; that must not fall back
+    to passes of the scan kernel (advisor finding), and an uncertifiable tie block (> 64 exact
+    duplicates) must come from the dense path, not from a truncated list."""
+    G = o.synth_l2_gallery(50_000, 128, seed=31)
+    G[100:200] = G[7]                       # 101 identical rows
+    enc = GalleryDict()
+    enc.bulk_load(["id%07d" % i for i in range(len(G))], G)
+    fs = FaceService(enc, tolerance=0.6, raise_errors=True)
+    Q, _ = o.synth_l2_queries(G, 12, seed=32)
+    Q[0] = G[7]
+    res = fs.batch_compare_faces(list(Q))
+    assert frp_b200.last_match_path() in ("gemm_tcgen05", "scan_f32")     # scan_f32 only for the ladder of query 0
+    ref = {n: g.tolist() for n, g in zip(enc.keys(), G)}
+    want = o.batch_compare_faces(ref, list(Q), 0.6)
+    for b in range(len(Q)):
+        assert [r["target"] for r in res[b]] == [r["target"] for r in want[b]], b
+        assert np.abs(np.array([r["distance"] for r in res[b]]) - np.array([r["distance"] for r in want[b]])).max(initial=0) < TIGHT
+    assert len(res[0]) >= 101
+    before = frp_b200.kernel_launches()
+    fs.batch_compare_faces(list(Q[1:9]))
+    assert frp_b200.last_match_path() == "gemm_tcgen05"
+    assert frp_b200.kernel_launches() - before <= 4            # prep + gemm + rerank (+ pad memset)
+
+
+# ----------------------------------------------------------------------------------------------
+# persistence
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [METRIC_COS, METRIC_L2])
+def test_snapshot_load_is_verbatim_and_answers_identically(tmp_path, metric):
+    rng = np.random.default_rng(5)
+    G = (rng.standard_normal((5000, 100)) * (3.0 if metric == METRIC_COS else 0.06)).astype(np.float32)
+    Q = (G[rng.integers(0, 5000, 9)] + rng.normal(0, 0.01, (9, 100))).astype(np.float32)
+    g = Gallery(100, metric)
+    g.append(G)
+    g.remove(17)
+    p = str(tmp_path / "snap.bin")
+    g.save(p)
+    assert not os.path.exists(p + ".tmp")
+    h = Gallery.load(p)
+    try:
+        for r in (0, 16, 4999):
+            assert np.array_equal(g.get_row(r), h.get_row(r))        # master bit-identical (no re-normalisation)
+        tau = 0.5 if metric == METRIC_COS else 0.6
+        for flags in (0, MATCH_FORCE_GEMM, MATCH_FORCE_SCAN, MATCH_NO_THRESHOLD):
+            a = g.match(Q, tau, 7, flags)
+            b = h.match(Q, tau, 7, flags)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y, equal_nan=True)
+        assert np.array_equal(g.scores(Q[:2]), h.scores(Q[:2]), equal_nan=True)
+        assert h.counts() == (5000, 4999)
+    finally:
+        h.close()
+    # corrupt headers and truncated files are refused before anything is allocated
+    raw = open(p, "rb").read()
+    for name, patch in (("dimp", (12, struct.pack("<i", 4096))), ("rows", (24, struct.pack("<Q", 1 << 39))),
+                        ("metric", (16, struct.pack("<i", 9)))):
+        bad = bytearray(raw)
+        bad[patch[0]:patch[0] + len(patch[1])] = patch[1]
+        q = str(tmp_path / ("bad_%s.bin" % name))
+        open(q, "wb").write(bytes(bad))
+        with pytest.raises(frp_b200.FrpError):
+            Gallery.load(q)
+    open(str(tmp_path / "short.bin"), "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(frp_b200.FrpError):
+        Gallery.load(str(tmp_path / "short.bin"))
+    g.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# N4: clustering on the device
+# ----------------------------------------------------------------------------------------------
+def test_cluster_faces_on_device_equals_the_reference_algorithm():
+    """>= 20 k x 128 faces in identity clusters, members spread over the whole row range, with
+    chains (A~B, B~C, A!~C) whose assignment depends on the greedy seed order, a cluster larger
+    than the 64-neighbour list (dense fallback) and deleted rows."""
+    G = o.synth_identity_gallery(1200, 17, seed=41, chain_every=40)
+    big = G[5] + np.random.default_rng(1).normal(0, 0.004, (90, 128))        # 91 faces within ~0.06
+    G = np.concatenate([G, big])
+    names = ["id%07d" % i for i in range(len(G))]
+    enc = GalleryDict()
+    enc.bulk_load(names, G)
+    fs = FaceService(enc, raise_errors=True)
+    for n in (names[3], names[5000], names[12345]):
+        del enc[n]
+    ref = {n: enc[n] for n in enc.keys()}
+    assert len(ref) >= 20_000
+    n_want = {}
+    for thr in (0.6, 0.45):
+        before = frp_b200.kernel_launches()
+        got = fs.cluster_faces(thr)
+        launches = frp_b200.kernel_launches() - before
+        want = o.cluster_faces(ref, thr)
+        n_want[thr] = len(want)
+        assert list(got.keys()) == list(want.keys())
+        assert got == want
+        assert max(len(v) for v in got.values()) >= 91
+        # slabs of 256 seeds: a few hundred launches, not one dense pass per seed
+        assert launches < 4 * (len(ref) // 256 + 1) + 64, launches
+    labels, n, stats = enc.gallery.cluster(0.6)
+    assert n == n_want[0.6] and stats["dense_fallbacks"] >= 1
+    assert stats["rows_matched"] <= len(G) and (labels[[3, 5000, 12345]] == -1).all()
+    # cosine galleries cluster by similarity >= threshold
+    Gc = o.synth_cos_gallery(3000, 512, seed=43)
+    Gc[1500:1520] = Gc[4] + 0.02 * o.synth_cos_gallery(20, 512, seed=44)
+    encc = GalleryDict(METRIC_COS)
+    encc.bulk_load(["c%d" % i for i in range(len(Gc))], Gc)
+    got = FaceService(encc, raise_errors=True).cluster_faces(0.8)
+    S = o.cosine_scores(Gc, Gc[4])[0]
+    assert got["cluster_4"] == ["c%d" % i for i in np.nonzero(S >= 0.8)[0]]
+    assert len(got) == 3000 - 20
+
+
+# ----------------------------------------------------------------------------------------------
+# N2: cooldown on the device
+# ----------------------------------------------------------------------------------------------
+def test_device_cooldown_equals_the_host_filter():
+    rng = np.random.default_rng(7)
+    G = o.synth_l2_gallery(30_000, 128, seed=51)
+    G[20_000] = G[40]                 # two gallery rows that match the same faces
+    enc = GalleryDict()
+    enc.bulk_load(["id%07d" % i for i in range(len(G))], G)
+    fs = FaceService(enc, raise_errors=True)
+    host = CooldownFilter(10.0)
+    dev = DeviceCooldown(capacity=4096, cooldown_seconds=10.0)
+    cams = [0, 1, 2, 7]
+    cfg = {1: {"confidence_threshold": 0.25}, 2: {"max_faces": 3}}
+    people = [40, 41, 42, 43, 44, 29_999]
+    now = 1000.0
+    total = 0
+    for tick in range(14):
+        faces = {}
+        for c in cams:
+            who = rng.choice(people, size=rng.integers(1, 6))
+            fl = [G[p] + rng.normal(0, 0.012 + 0.01 * (c == 1), 128) for p in who]
+            if tick % 3 == 0:
+                fl.append(fl[0].copy())                   # the same person twice in one frame
+            fl.append(rng.normal(0, 0.05, 128))           # an impostor
+            faces[c] = fl
+        want = host.filter(scan_cameras(fs, faces, cfg), now)
+        before = frp_b200.kernel_launches()
+        got = scan_cameras_recorded(fs, dev, faces, cfg, now)
+        assert frp_b200.kernel_launches() - before <= 5
+        assert list(got.keys()) == list(want.keys())
+        for c in cams:
+            assert [(d["target"], d["confidence"]) for d in got[c]] == [(d["target"], d["confidence"]) for d in want[c]], (tick, c)
+            assert np.allclose([d["distance"] for d in got[c]], [d["distance"] for d in want[c]], atol=TIGHT)
+            total += len(got[c])
+        now += float(rng.choice([0.5, 3.0, 11.0]))
+    assert total > 40
+    # raw API: limit NaN = no second filter, hits ordered by (query, rank), clear() forgets
+    q = (G[[40, 41, 40]] + rng.normal(0, 0.01, (3, 128))).astype(np.float32)
+    dev.clear()
+    h = dev.match_hits(enc.gallery, q, 0.6, 5, [3, 3, 3], [np.nan, 0.0, np.nan], now=5.0)
+    assert h["query"].tolist() == [0, 0] and h["row"].tolist() == [40, 20_000] and (h["camera"] == 3).all()
+    assert len(dev.match_hits(enc.gallery, q, 0.6, 5, [3, 3, 3], None, now=6.0)) == 1        # only person 41 is new
+    assert len(dev.match_hits(enc.gallery, q, 0.6, 5, [3, 3, 3], None, now=15.5)) == 2       # 40 / 20 000 cooled down, 41 not
+    dev.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# N1: micro-batching front end
+# ----------------------------------------------------------------------------------------------
+def test_batching_matcher_coalesces_concurrent_callers():
+    """The reference's 4 worker threads (routes/camera.py:29) each calling the per-face match:
+    results identical to serial calls, >= 3x fewer kernel launches."""
+    G = o.synth_l2_gallery(200_000, 128, seed=61)
+    enc = GalleryDict()
+    enc.bulk_load(["id%07d" % i for i in range(len(G))], G)
+    fs = FaceService(enc, raise_errors=True)
+    T, per = 4, 64
+    Q, _ = o.synth_l2_queries(G, T * per, seed=62)
+    Q = Q.astype(np.float32)
+    fs.match_topk(Q[:1], 0.6, 5)
+    before = frp_b200.kernel_launches()
+    serial = [fs.match_topk(q[None], 0.6, 5)[0] for q in Q]
+    serial_cam = [r for r in (fs.compare_faces(q) for q in Q[:8])]
+    serial_launches = frp_b200.kernel_launches() - before
+    bm = BatchingMatcher(fs, window_s=2e-3)
+    out = [None] * (T * per)
+    cam_out = [None] * 8
+    start = threading.Barrier(T)
+
+    def worker(t):
+        start.wait()
+        for i in range(t * per, (t + 1) * per):
+            out[i] = bm.match_topk(Q[i], 0.6, 5)
+        for i in range(t * 2, t * 2 + 2):
+            cam_out[i] = bm.camera_matches(Q[i], camera_id=t, confidence_threshold=0.5)
+
+    before = frp_b200.kernel_launches()
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    batched_launches = frp_b200.kernel_launches() - before
+    assert out == serial
+    for i in range(8):
+        want = [{"camera_id": i // 2, "target": r["target"], "distance": r["distance"], "confidence": r["confidence"]}
+                for r in serial_cam[i] if r["match"] and r["distance"] <= 0.5]
+        assert [(d["camera_id"], d["target"], d["confidence"]) for d in cam_out[i]] == \\
+            [(d["camera_id"], d["target"], d["confidence"]) for d in want]
+        assert np.allclose([d["distance"] for d in cam_out[i]], [d["distance"] for d in want], atol=TIGHT)
+    assert bm.queries == T * per + 8
+    assert serial_launches >= 3 * batched_launches, (serial_launches, batched_launches, bm.batches)
+
+
+# ----------------------------------------------------------------------------------------------
+# 8e: mutable row-sharded gallery
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [METRIC_L2, METRIC_COS])
+def test_sharded_dict_mutations_equal_one_dict(metric):
+    """A random store / update / delete / rename stream applied to 1, 2 and 8 shards gives the
+    answers of a single GalleryDict and of a plain Python dict run through the oracle."""
+    rng = np.random.default_rng(71)
+    dim = 128 if metric == METRIC_L2 else 64
+    pool = ["p%03d" % i for i in range(160)]
+    base = rng.normal(0, 0.05, (len(pool), dim))
+    base[1::2] = base[0::2]                      # every identity twice under different names: exact ties
+    shards = {R: ShardedGalleryDict(R, dim, metric) for R in (1, 2, 8)}
+    single = GalleryDict(metric)
+    ref = {}
+    tau, k = (0.6, 12) if metric == METRIC_L2 else (0.7, 12)
+
+    def check():
+        if not ref:
+            return
+        names = list(ref.keys())
+        E = np.array([ref[n] for n in names])
+        Q = (E[rng.integers(0, len(E), 7)] + rng.normal(0, 0.003, (7, dim))).astype(np.float32)
+        if metric == METRIC_L2:
+            widx, wsc, wcnt = o.l2_match_topk(E.astype(np.float32), Q, tau, k, True)
+        else:
+            widx, wsc, wcnt = o.cos_match_topk(E.astype(np.float32), Q, tau, k, True)
+        want = [[names[i] for i in widx[b, :wcnt[b]]] for b in range(len(Q))]
+        idx, sc, cnt, _ = single.gallery.match(Q, tau, k)
+        assert [[single.name_of(int(i)) for i in idx[b, :cnt[b]]] for b in range(len(Q))] == want
+        for R, d in shards.items():
+            got, s, c, level = d.match(Q, tau, k)
+            assert got == want, (R, got, want)
+            assert np.array_equal(c, cnt) and level <= 2
+            assert np.array_equal(s, sc, equal_nan=True), R          # bit-identical scores for every shard count
+
+    for step in range(260):
+        op = rng.random()
+        n = pool[rng.integers(len(pool))]
+        if op < 0.6 or len(ref) < 8:
+            v = (base[pool.index(n)] + (rng.normal(0, 0.001, dim) if n in ref else 0)).tolist()
+            ref[n] = v
+            single[n] = v
+            for d in shards.values():
+                d[n] = v
+        elif op < 0.85:
+            if n in ref:
+                del ref[n]
+                del single[n]
+                for d in shards.values():
+                    del d[n]
+        else:
+            if n in ref:
+                new = n + "r%d" % step
+                v = ref.pop(n)
+                ref[new] = v
+                single.pop(n)
+                single[new] = v
+                for d in shards.values():
+                    d.rename(n, new, v)
+                pool[pool.index(n)] = new
+        if step % 20 == 19:
+            for d in shards.values():
+                assert d.keys() == list(ref.keys())
+            check()
+    live = shards[8].live_per_shard()
+    assert sum(live) == len(ref) and min(live) >= 1, live          # least-full routing: no shard starves
+    check()
+    for d in shards.values():
+        d.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# concurrency (advisor findings)
+# ----------------------------------------------------------------------------------------------
+def test_scores_never_overrun_while_the_gallery_grows():
+    """frp_scores reads the row count and fills the buffer under one lock; Gallery.scores sizes
+    its result from the count the call returns."""
+    g = Gallery(128, METRIC_L2)
+    rng = np.random.default_rng(3)
+    g.append(rng.normal(0, 0.05, (2000, 128)))
+    stop = threading.Event()
+    errs = []
+
+    def grower():
+        try:
+            while not stop.is_set():
+                g.append(rng.normal(0, 0.05, (97, 128)))
+        except Exception as e:       # pragma: no cover
+            errs.append(e)
+
+    t = threading.Thread(target=grower)
+    t.start()
+    q = rng.normal(0, 0.05, (3, 128)).astype(np.float32)
+    last = 0
+    try:
+        for _ in range(200):
+            s = g.scores(q)
+            assert s.shape[0] == 3 and s.shape[1] >= last and s.shape[1] <= g.rows
+            assert np.isfinite(s).all()
+            last = s.shape[1]
+    finally:
+        stop.set()
+        t.join()
+    assert not errs and last > 2000
+    # explicit capacity contract of the ABI
+    import ctypes as C
+    from frp_b200 import _capi
+    out = np.empty((1, 10), np.float64)
+    got = C.c_uint64(0)
+    rc = _capi.lib.frp_scores(g.handle, _capi.ptr(q), 1, _capi.ptr(out), 10, C.byref(got))
+    assert rc == _capi.FRP_E_RANGE and got.value == g.rows
+    g.close()
+
+
+def test_compaction_and_readers_do_not_race():
+    """GalleryDict.compact() swaps the device gallery and renumbers rows; readers hold the read
+    lock across subset -> native call -> name_of, so they never see a closed gallery, a missed
+    match or a wrong name (advisor finding)."""
+    G = o.synth_l2_gallery(6000, 128, seed=81)
+    enc = GalleryDict(compact_ratio=0.05)
+    names = ["id%07d" % i for i in range(len(G))]
+    enc.bulk_load(names, G)
+    fs = FaceService(enc, raise_errors=True)
+    keep = names[-50:]
+    stop = threading.Event()
+    errs = []
+
+    def reader(seed):
+        r = np.random.default_rng(seed)
+        try:
+            while not stop.is_set():
+                j = int(r.integers(0, 50))
+                row = len(G) - 50 + j
+                res = fs.match_topk(G[row][None].astype(np.float32), 0.3, 3)[0]
+                assert res and res[0][0] == keep[j] and res[0][1] < 1e-3, (res, keep[j])
+                bc = fs.batch_compare_faces([G[row], G[row]])
+                assert bc[0][0]["target"] == keep[j]
+        except Exception as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=reader, args=(s,)) for s in range(3)]
+    for x in th:
+        x.start()
+    try:
+        for n in names[:-50]:
+            del enc[n]                    # crosses the compaction trigger several times
+    finally:
+        stop.set()
+        for x in th:
+            x.join()
+    assert not errs, errs[:1]
+    assert len(enc) == 50 and enc.gallery.rows <= 1100
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_thread_two_devices():
+    """Per-device opt-in of large dynamic shared memory (advisor finding): the same thread runs
+    every kernel family on device 0 and then on device 1."""
+    G = o.synth_cos_gallery(40_000, 512, seed=5)
+    Q, _ = o.synth_cos_queries(G, 9, seed=6)
+    want = o.cos_match_topk(G, Q, 0.3, 10, True)
+    frames = o.synth_frames(1, 360, 640, seed=5)
+    fi, lm = o.synth_detections(1, 8, 360, 640, seed=6, sigma_range=(0.5, 1.5))
+    blobs = []
+    for dev in (0, 1):
+        g = Gallery(512, METRIC_COS, device=dev)
+        g.append(G)
+        for flags in (0, MATCH_FORCE_SCAN, MATCH_FORCE_GEMM):
+            idx, sc, cnt, st = g.match(Q, 0.3, 10, flags)
+            assert np.array_equal(idx, want[0])
+        g.close()
+        blobs.append(frp_b200.align.norm_crop_batch(frames, fi, lmk=lm, device=dev)[0])
+    assert np.array_equal(blobs[0], blobs[1])
