@@ -335,8 +335,8 @@ def test_batching_matcher_coalesces_concurrent_callers():
     for i in range(8):
         want = [{"camera_id": i // 2, "target": r["target"], "distance": r["distance"], "confidence": r["confidence"]}
                 for r in serial_cam[i] if r["match"] and r["distance"] <= 0.5]
-        assert [(d["camera_id"], d["target"], d["confidence"]) for d in cam_out[i]] == \\
-            [(d["camera_id"], d["target"], d["confidence"]) for d in want]
+        got_i = [(d["camera_id"], d["target"], d["confidence"]) for d in cam_out[i]]
+        assert got_i == [(d["camera_id"], d["target"], d["confidence"]) for d in want]
         assert np.allclose([d["distance"] for d in cam_out[i]], [d["distance"] for d in want], atol=TIGHT)
     assert bm.queries == T * per + 8
     assert serial_launches >= 3 * batched_launches, (serial_launches, batched_launches, bm.batches)
