@@ -124,7 +124,7 @@ int match_device_locked(frp_gallery* g, const float* q_dev, size_t qstride, cons
         return FRP_OK;
     }
     const bool exact = (flags & FRP_MATCH_FORCE_EXACT) != 0;
-    const bool wide = (flags & FRP_MATCH_WIDE) != 0 || KP > 32;
+    const bool wide = (flags & FRP_MATCH_WIDE) != 0;      // the ladder's last rung: 64-key lists on the scan kernel
     bool use_gemm = false;
     if (!exact && !wide && gemm_supported(g)) {
         // B > 4: tensor cores.  B <= 4 is HBM-bound on either kernel; on large galleries the
@@ -322,8 +322,10 @@ int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, 
     const size_t ib = (size_t)B * k * sizeof(int64_t), sb = (size_t)B * k * sizeof(float);
     const size_t cb = (size_t)B * sizeof(int32_t);
 
+    // small batches are staged (a 2 KB memcpy is cheaper than asking the driver whether the
+    // caller's buffer is pinned); large pinned batches are copied from where they are
     const void* qsrc = queries;
-    if (!is_pinned_host(queries)) { memcpy(h + L.off_q, queries, qb); qsrc = h + L.off_q; }
+    if (qb <= 65536 || !is_pinned_host(queries)) { memcpy(h + L.off_q, queries, qb); qsrc = h + L.off_q; }
     cudaError_t e = cudaMemcpyAsync(dq, qsrc, qb, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
         rc = match_device_locked(g, dq, (size_t)g->dim, nullptr, B, tau, k, flags, pick_kp(k), di, ds, nullptr, dc, dt, st);
