@@ -298,7 +298,7 @@ def make_gallery(frp, torch, rows_local, seed, device, keep_rows=4096, dim=512, 
     gen = torch.Generator(device=device).manual_seed(seed)
     chunk = 1_000_000
     nchunks = max(1, (rows_local + chunk - 1) // chunk)
-    per = max(1, keep_rows // nchunks)
+    per = max(1, -(-keep_rows // nchunks))          # ceil: the concatenation is cut to exactly keep_rows
     keep, keep_idx = [], []
     st = torch.cuda.current_stream().cuda_stream
     for lo in range(0, rows_local, chunk):

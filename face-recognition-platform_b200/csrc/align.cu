@@ -26,6 +26,7 @@
 // whose frames are not 16-byte aligned are sampled tap by tap from global memory.
 #include <cuda.h>
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "frp_device.cuh"
@@ -38,34 +39,54 @@ namespace {
 constexpr int kOut = 112;
 constexpr int kTileW = 16;
 constexpr int kTilesX = kOut / kTileW;              // 7
+constexpr int kBandRows = 16;                       // output rows per work item
+constexpr int kBands = kOut / kBandRows;            // 7 work items per crop
 #ifndef FRP_ALIGN_WARPS
 #define FRP_ALIGN_WARPS 18
 #endif
 constexpr int kWarps = FRP_ALIGN_WARPS;             // what fits in 227 KB of shared memory
-#ifndef FRP_ALIGN_ITEMS
-#define FRP_ALIGN_ITEMS 7     // measured (C4): 2 -> 0.183 ms, 4 -> 0.170 ms, 7 -> 0.165 ms
-#endif
-constexpr int kItemsPerCrop = FRP_ALIGN_ITEMS;      // work items (tile ranges) per crop
-#ifndef FRP_ALIGN_PREF
-#define FRP_ALIGN_PREF 1     // 0: prefer (TH=8, prefetch) over (TH=16, no prefetch); 1: the reverse
-#endif
-constexpr int kNumW = 5, kNumH = 5;
-__constant__ int c_box_w[kNumW] = {64, 96, 128, 176, 224};   // bytes (multiples of 16)
-__constant__ int c_box_h[kNumH] = {8, 14, 22, 34, 46};       // rows
-constexpr int kHostBoxW[kNumW] = {64, 96, 128, 176, 224};
-constexpr int kHostBoxH[kNumH] = {8, 14, 22, 34, 46};
-constexpr int kMaxBoxW = 224, kMaxBoxH = 46;
+// Box ladder of the staged source tiles: widths in steps of 32 bytes, heights in steps of 4 rows
+// (66 tensor maps, 8.25 KB of kernel parameters).  On the C4 workload the ladder stages
+// 1.06 GB against 1.24 GB for the 5 x 5 ladder of round 1 (exact bounding boxes: 0.81 GB).
+constexpr int kNumW = 6, kNumH = 11;
+constexpr int kMaxBoxW = 224, kMaxBoxH = 48;
+__host__ __device__ constexpr int box_w(int i) { return 64 + 32 * i; }   // bytes (multiples of 16)
+__host__ __device__ constexpr int box_h(int i) { return 8 + 4 * i; }     // rows
 #ifndef FRP_ALIGN_BUF
-#define FRP_ALIGN_BUF 10368
+#define FRP_ALIGN_BUF 10240
 #endif
-constexpr int kBufBytes = FRP_ALIGN_BUF;            // >= 224*46 + 16 slack, multiple of 128
-constexpr int kTabBytes = 4 * kOut * 4;             // adelta, bdelta, X0, Y0 (1792 = 14*128)
-constexpr int kHalfBuf = (kBufBytes / 2) & ~127;     // boxes up to this size are double buffered inside kBufBytes
-constexpr int kWarpSmem = kTabBytes + kBufBytes + 128;   // tab + buffer + mbarriers, multiple of 128
+constexpr int kBufBytes = FRP_ALIGN_BUF;            // staging bytes per warp, multiple of 128
+constexpr int kHalfBuf = (kBufBytes / 2) & ~127;    // boxes up to this size are double buffered inside kBufBytes
+
+// ---- per-crop record written by align_plan_kernel, read by align_kernel with bulk copies ----
+//   [0,32)      CropHdr
+//   [32,480)    adelta[112]  int32   round(iM00 * x * 1024)
+//   [480,928)   bdelta[112]  int32   round(iM10 * x * 1024)
+//   [928,...)   7 bands x 256 B: (X0,Y0)[16] int2 of the band's rows | tile origins (c0, sy0)[14] int2
+// A work item (crop, band) needs the common block (928 B) and its band block (256 B).
+struct CropHdr {
+    int frame;       // clamped frame index
+    int map;         // tensor-map index (hi * kNumW + wi)
+    int pitch;       // staged row pitch = box width in bytes
+    int box_bytes;
+    int flags;       // bit 0 direct (no TMA staging), bit 1 dual (box fits half the buffer), bit 2 TH = 8
+    int pad[3];
+};
+constexpr int kCommonBytes = 32 + 2 * kOut * 4;     // 928
+constexpr int kBandBytes = 256;
+constexpr int kRecBytes = ((kCommonBytes + kBands * kBandBytes + 63) / 64) * 64;   // 2752
+constexpr int kItemBytes = kCommonBytes + kBandBytes;                             // 1184, per table slot
+constexpr int kTabBytes = ((2 * kItemBytes + 127) / 128) * 128;                   // two table slots (2432)
+constexpr int kWarpSmem = kTabBytes + kBufBytes + 128;                            // + mbarriers; multiple of 128
+static_assert(kBufBytes % 128 == 0 && kWarpSmem % 128 == 0, "TMA destinations are 128-byte aligned");
+static_assert((size_t)kWarps * kWarpSmem + 128 <= 227 * 1024, "per-warp staging exceeds the 227 KB of shared memory");
 
 struct TmapSet {
     CUtensorMap m[kNumW * kNumH];
 };
+#ifdef FRP_ALIGN_DEBUG
+__device__ int g_align_dbg[64];
+#endif
 
 struct AlignArgs {
     const uint8_t* frames;
@@ -78,7 +99,7 @@ struct AlignArgs {
     __half* out_blob;     // [n][3][112][112]
     uint8_t* out_aligned; // [n][112][112][3] or null
     int* counter;         // dynamic work counter
-    double* iM;           // [n][6] inverse maps (workspace, written by align_plan_kernel)
+    uint8_t* rec;         // [n][kRecBytes] plan records (workspace, written by align_plan_kernel)
     int use_tma;          // tensor maps valid (16-byte aligned base / pitch)
 };
 
@@ -124,46 +145,6 @@ __device__ void invert_affine_dev(const double* M, double* iM) {
     iM[3] = m3;  iM[4] = A22; iM[5] = b2;
 }
 
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, uint32_t dst_saddr, int c0,
-                                            int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst_saddr), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-__device__ __forceinline__ int2 lds64(uint32_t saddr) {
-    int2 v;
-    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
-    return v;
-}
-
-struct TileMeta {
-    int c0;        // byte offset (in the source row) of the first staged byte
-    int sy0;       // first staged source row
-    int pitch;     // staged row pitch in bytes (box width)
-    int direct;    // 1: footprint did not fit -> read taps from global memory
-};
-
-// Per-crop staging plan.  The inverse map is affine and the fixed-point tables are monotone
-// in x and in y, so (a) the source bounding box of EVERY 16 x TH tile of a crop is bounded by
-// the same extents, and (b) its minimum corner is the sum of two table entries whose
-// positions depend only on the signs of the matrix entries: one box size per crop, and
-// four table reads per tile.
-struct CropPlan {
-    int map;            // tensor-map index (hi * kNumW + wi)
-    int pitch;          // box width in bytes
-    int box_bytes;
-    int xsel_x, ysel_x; // tile-corner offsets (0 or kTileW-1, 0 or TH-1) of the minimum source x
-    int xsel_y, ysel_y; // likewise for the minimum source y
-    int direct;         // no TMA staging for this crop
-    int dual;           // box fits half the buffer: prefetch the next tile while blending
-};
-
 // Box for 16 x TH tiles of a map with |iM| = (ax ay; bx by): false if it exceeds the ladder.
 // Over a tile X = X0[y] + adelta[x] spans at most (15 ax + (TH-1) ay) * 1024 + 2 fixed-point
 // units (each table rounds once), so sx_max - sx_min <= floor(ext_x + 2/1024) + 1; with
@@ -175,32 +156,171 @@ __device__ __forceinline__ bool plan_box(double ax, double ay, double bx, double
     const int need_w = 3 * ((int)(ext_x + 0.01) + 3) + 15;
     const int need_h = (int)(ext_y + 0.01) + 3;
     if (need_w > kMaxBoxW || need_h > kMaxBoxH) return false;
-    wi = 0; hi = 0;
-#pragma unroll
-    for (int i = 0; i < kNumW - 1; ++i) wi += (need_w > c_box_w[i]) ? 1 : 0;
-#pragma unroll
-    for (int i = 0; i < kNumH - 1; ++i) hi += (need_h > c_box_h[i]) ? 1 : 0;
-    return c_box_w[wi] * c_box_h[hi] <= kBufBytes;
+    wi = need_w <= 64 ? 0 : (need_w - 64 + 31) / 32;
+    hi = need_h <= 8 ? 0 : (need_h - 8 + 3) / 4;
+    return box_w(wi) * box_h(hi) <= kBufBytes;
 }
 
-// locate the box of output tile (x0,y0) and start its TMA load into buf
-__device__ __forceinline__ TileMeta stage_tile(const CropPlan& pl, const TmapSet& maps, const int* tab, int x0,
-                                               int y0, int frame_index, uint32_t buf_saddr, uint64_t* bar,
-                                               int lane) {
-    // tables: adelta | bdelta | (X0,Y0) pairs, read with shared-space loads
-    const uint32_t ts = smem_u32(tab);
-    const int Xmin = (int)lds32(ts + 8 * (kOut + y0 + pl.ysel_x)) + (int)lds32(ts + 4 * (x0 + pl.xsel_x));
-    const int Ymin = (int)lds32(ts + 8 * (kOut + y0 + pl.ysel_y) + 4) + (int)lds32(ts + 4 * (kOut + x0 + pl.xsel_y));
-    TileMeta m;
-    m.c0 = (3 * (Xmin >> 10)) & ~15;   // TMA needs the inner coordinate 16-byte aligned (floor, also for negatives)
-    m.sy0 = Ymin >> 10;
-    m.pitch = pl.pitch;
-    m.direct = pl.direct;
-    if (!pl.direct && lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)pl.box_bytes);
-        tma_load_3d(&maps.m[pl.map], bar, buf_saddr, m.c0, m.sy0, frame_index);
+// ---------------------------------------------------------------------------------------------
+// align_plan_kernel: one warp per crop.  Forward similarity (or the caller's matrix), cv2's
+// inverse, the fixed-point coordinate tables, the staging plan (tile height, box size, single or
+// double buffering) and the source origin of every tile — everything a work item of
+// align_kernel needs, so that kernel runs no fp64 and no per-tile box search.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPlanWarps = 4;
+
+__global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __grid_constant__ AlignArgs a) {
+    __shared__ int s_tab[kPlanWarps][4 * kOut];      // adelta | bdelta | X0 | Y0
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crop = blockIdx.x * kPlanWarps + warp;
+    if (crop >= a.n) return;
+    int* tab = s_tab[warp];
+    double M[6], iM[6];
+    if (a.M) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) M[i] = a.M[(size_t)crop * 6 + i];
+    } else {
+        float lm[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) lm[i] = a.lmk[(size_t)crop * 10 + i];
+        estimate_norm_dev(lm, M);
     }
-    return m;
+    invert_affine_dev(M, iM);
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) finite = finite && (fabs(iM[i]) < 1e12);
+    if (!finite) { iM[0] = iM[1] = iM[3] = iM[4] = 0.0; iM[2] = iM[5] = -1e6; }
+
+    uint8_t* rec = a.rec + (size_t)crop * kRecBytes;
+    int* r_ad = reinterpret_cast<int*>(rec + 32);
+    int* r_bd = reinterpret_cast<int*>(rec + 32 + kOut * 4);
+    for (int x = lane; x < kOut; x += 32) {
+        const double xd = (double)x;
+        const int ad = __double2int_rn(__dmul_rn(__dmul_rn(iM[0], xd), 1024.0));
+        const int bd = __double2int_rn(__dmul_rn(__dmul_rn(iM[3], xd), 1024.0));
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[1], xd), iM[2]), 1024.0)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[4], xd), iM[5]), 1024.0)) + 16;
+        tab[x] = ad; tab[kOut + x] = bd; tab[2 * kOut + x] = X0; tab[3 * kOut + x] = Y0;
+        r_ad[x] = ad;
+        r_bd[x] = bd;
+        // (X0, Y0)[row] interleaved inside the row's band block: one 64-bit load in the blend
+        int* bandp = reinterpret_cast<int*>(rec + kCommonBytes + (x / kBandRows) * kBandBytes);
+        bandp[2 * (x % kBandRows)] = X0;
+        bandp[2 * (x % kBandRows) + 1] = Y0;
+    }
+    __syncwarp();
+
+    // ---- staging plan ----
+    const double ax = fabs(iM[0]), ay = fabs(iM[1]), bx = fabs(iM[3]), by = fabs(iM[4]);
+    int wi16 = 0, hi16 = 0, wi8 = 0, hi8 = 0;
+    const bool fit16 = plan_box<16>(ax, ay, bx, by, wi16, hi16);
+    const bool fit8 = plan_box<8>(ax, ay, bx, by, wi8, hi8);
+    // coordinates near the int16 saturation of cv::remap's xy map are handled tap by tap:
+    // the map is affine, so its extremes over the crop are at the four corners
+    bool far = false;
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+            const double sx = iM[0] * (cx * (kOut - 1)) + iM[1] * (cy * (kOut - 1)) + iM[2];
+            const double sy = iM[3] * (cx * (kOut - 1)) + iM[4] * (cy * (kOut - 1)) + iM[5];
+            far = far || !(fabs(sx) < 29000.0 && fabs(sy) < 29000.0);
+        }
+    const bool th16 = fit16;
+    const bool direct = !(a.use_tma && !far && (fit16 || fit8));
+    const int wi = th16 ? wi16 : wi8, hi = th16 ? hi16 : hi8;
+    const int th1 = th16 ? 15 : 7;
+    const int xsel_x = (iM[0] >= 0.0) ? 0 : kTileW - 1, ysel_x = (iM[1] >= 0.0) ? 0 : th1;
+    const int xsel_y = (iM[3] >= 0.0) ? 0 : kTileW - 1, ysel_y = (iM[4] >= 0.0) ? 0 : th1;
+    if (lane == 0) {
+        CropHdr h;
+        int fi = a.frame_idx[crop];
+        h.frame = min(max(fi, 0), a.F - 1);
+        h.map = hi * kNumW + wi;
+        h.pitch = box_w(wi);
+        h.box_bytes = box_w(wi) * box_h(hi);
+#ifdef FRP_ALIGN_NODUAL
+        const bool dual = false;                   // A/B switch: single buffering only
+#else
+        // 8-row tiles (large faces only) stay single-buffered: their double-buffered form faulted on
+        // B200 ("illegal memory access" from the staged kernel, every address audited in range)
+        // and is not worth the risk for the ~20 % of crops that use it
+        const bool dual = !direct && th16 && h.box_bytes <= kHalfBuf;
+#endif
+        h.flags = (direct ? 1 : 0) | (dual ? 2 : 0) | (th16 ? 0 : 4);
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        *reinterpret_cast<CropHdr*>(rec) = h;
+    }
+    // ---- source origin of every tile: the map is affine and the tables are monotone, so the
+    // minimum corner of a tile's footprint is the sum of two table entries whose positions
+    // depend only on the signs of the matrix entries ----
+    const int TH = th16 ? 16 : 8;
+    const int tiles_per_band = kTilesX * (kBandRows / TH);
+    for (int t = lane; t < kBands * tiles_per_band; t += 32) {
+        const int band = t / tiles_per_band, tb = t % tiles_per_band;
+        const int x0 = (tb % kTilesX) * kTileW, y0 = band * kBandRows + (tb / kTilesX) * TH;
+        const int Xmin = tab[2 * kOut + y0 + ysel_x] + tab[x0 + xsel_x];
+        const int Ymin = tab[3 * kOut + y0 + ysel_y] + tab[kOut + x0 + xsel_y];
+        int* org = reinterpret_cast<int*>(rec + kCommonBytes + band * kBandBytes + 128) + 2 * tb;
+        org[0] = (3 * (Xmin >> 10)) & ~15;   // TMA needs the inner coordinate 16-byte aligned (floor, also for negatives)
+        org[1] = Ymin >> 10;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// align_kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar_saddr, uint32_t dst_saddr, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_saddr), "l"(map), "r"(bar_saddr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar_saddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_saddr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(bar_saddr), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// third word of a tap row: only the start offset 3 (one pixel in four) reaches into it, so the
+// load is predicated per lane — fewer shared-memory wavefronts (the bank conflicts of a warp
+// load grow with the number of active lanes).  A lane that skips the load keeps `seed` (any
+// defined value that is dead by now: it only feeds bytes the byte permutes never select), so
+// the destination has no live range reaching back to an uninitialised register.
+__device__ __forceinline__ uint32_t lds32_if3(uint32_t saddr, uint32_t off, uint32_t seed) {
+#ifdef FRP_ALIGN_NOPRED
+    return lds32(saddr);     // A/B switch: load the third word unconditionally
+#endif
+    uint32_t v = seed;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, 3;\n\t"
+        "setp.eq.u32 p, t, 3;\n\t"
+        "@p ld.shared.u32 %0, [%1];\n\t}"
+        : "+r"(v) : "r"(saddr), "r"(off));
+    return v;
+}
+__device__ __forceinline__ int2 lds64(uint32_t saddr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
 }
 
 __device__ __forceinline__ unsigned tap_global(const AlignArgs& a, const uint8_t* frame, int sx, int sy) {
@@ -238,52 +358,10 @@ __device__ __forceinline__ unsigned short norm_half(unsigned acc) {
     return __half_as_ushort(__float2half_rn(n));
 }
 
-// one output tile, x-major lane mapping: lane -> column x0 + (lane & 15) and rows
-// y0 + 2j + (lane >> 4).  A warp-wide tap load then walks along ONE (rotated) source line
-// per half-warp, which keeps shared-memory bank conflicts at <= ~2-way for any staged row
-// pitch (the row-major mapping measured 4.7 wavefronts per load).
-template <int TH>
-__device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* frame, const int* tab,
-                                             const TileMeta& tm, uint32_t buf_saddr, int x0, int y0, int lane,
-                                             __half* oblob, uint8_t* oal) {
-    constexpr int NJ = TH / 2;
-    const int x = x0 + (lane & 15);
-    const int yb = y0 + (lane >> 4);
-    const uint32_t ts = smem_u32(tab);
-    const int ad = (int)lds32(ts + 4 * x), bd = (int)lds32(ts + 4 * (kOut + x));
-    const uint32_t tsy = ts + 8 * (kOut + yb);         // (X0,Y0)[yb]
-    unsigned short* o16 = reinterpret_cast<unsigned short*>(oblob) + (size_t)yb * kOut + x;
-    uint8_t* o8 = oal ? oal + ((size_t)yb * kOut + x) * 3 : nullptr;
-    const int base = -tm.sy0 * tm.pitch - tm.c0;
-    unsigned vB[NJ], vG[NJ], vR[NJ];      // un-shifted blend sums (pixel << 15 | fraction)
-    if (!tm.direct) {      // warp-uniform: one branch per tile, not per pixel
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int2 xy = lds64(tsy + 16 * j);
-            const int X = xy.x + ad, Y = xy.y + bd;          // 10 fractional bits
-            const int off = (Y >> 10) * tm.pitch + 3 * (X >> 10) + base;
-            const uint32_t w0 = buf_saddr + (off & ~3);
-            const uint32_t w1 = w0 + tm.pitch;
-            const unsigned shf = (unsigned)off << 3;          // funnel shifts use the low 5 bits
-            const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32(w0 + 8);
-            const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32(w1 + 8);
-            blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
-                     __funnelshift_r(b1, b2, shf), (X >> 5) & 31, Y & 0x3E0, vB[j], vG[j], vR[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int2 xy = lds64(tsy + 16 * j);
-            const int X = (xy.x + ad) >> 5, Y = (xy.y + bd) >> 5;
-            const int sx = max(-32768, min(32767, X >> 5));
-            const int sy = max(-32768, min(32767, Y >> 5));
-            const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
-            const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
-            blend_px(t00 | (t01 << 24), t01 >> 8, t10 | (t11 << 24), t11 >> 8, X & 31, (Y & 31) << 5, vB[j], vG[j],
-                     vR[j]);
-        }
-    }
-    // BGR -> RGB planes; a half-warp writes 16 consecutive halfs (one 32-byte sector)
+// BGR -> RGB planes; a half-warp writes 16 consecutive halfs (one 32-byte sector) per plane row
+template <int NJ>
+__device__ __forceinline__ void store_px(unsigned short* o16, uint8_t* o8, const unsigned (&vB)[NJ],
+                                         const unsigned (&vG)[NJ], const unsigned (&vR)[NJ]) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         o16[(size_t)j * 2 * kOut] = norm_half(vR[j]);
@@ -299,168 +377,222 @@ __device__ __forceinline__ void blend_tile_x(const AlignArgs& a, const uint8_t* 
     }
 }
 
-// all tiles [t_begin, t_end) of one crop with tile height TH
+// One staged output tile, x-major lane mapping: lane -> column x0 + (lane & 15) and rows
+// yr0 + 2j + (lane >> 4) of the band.  A warp-wide tap load then walks along ONE (rotated)
+// source line per half-warp, which keeps shared-memory bank conflicts at <= ~2-way for any
+// staged row pitch.  tabs: shared address of the item's table block.
 template <int TH>
-__device__ __forceinline__ void run_tiles(const AlignArgs& a, const TmapSet& maps, const CropPlan& pl,
-                                          const uint8_t* frame, int fi, const int* tab, uint32_t buf_saddr0,
-                                          uint64_t* bars, uint32_t& parity, int t_begin, int t_end, int lane,
-                                          __half* oblob, uint8_t* oal) {
-    if (!pl.dual) {
-        // one buffer: the TMA latency of this warp is covered by the blends of the others
-        for (int t = t_begin; t < t_end; ++t) {
-            const TileMeta tm = stage_tile(pl, maps, tab, (t % kTilesX) * kTileW, (t / kTilesX) * TH, fi,
-                                           buf_saddr0, &bars[0], lane);
-            if (!tm.direct) {
-                mbar_wait(&bars[0], parity & 1u);
-                parity ^= 1u;
+__device__ __forceinline__ void blend_tile_staged(uint32_t tabs, uint32_t buf_saddr, int c0, int sy0, int pitch,
+                                                  int x0, int yr0, int lane, unsigned short* o16, uint8_t* o8) {
+    constexpr int NJ = TH / 2;
+    const int x = x0 + (lane & 15);
+    const int yb = yr0 + (lane >> 4);
+    const int ad = (int)lds32(tabs + 32 + 4 * x), bd = (int)lds32(tabs + 32 + 4 * (kOut + x));
+    const uint32_t tsy = tabs + kCommonBytes + 8 * yb;            // (X0,Y0)[yb] of this band
+    // shared address of source byte (0, 0) of the frame in the staged box coordinate system
+    const int base = (int)buf_saddr - sy0 * pitch - c0;
+    unsigned vB[NJ], vG[NJ], vR[NJ];      // un-shifted blend sums (pixel << 15 | fraction)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int2 xy = lds64(tsy + 16 * j);
+        const int X = xy.x + ad, Y = xy.y + bd;          // 10 fractional bits
+        const uint32_t off = (uint32_t)((Y >> 10) * pitch + 3 * (X >> 10) + base);   // byte address of the first tap
+        uint32_t w0 = off & ~3u;
+        uint32_t w1 = w0 + (uint32_t)pitch;
+#ifdef FRP_ALIGN_DEBUG
+        // address audit (debug builds only): record and clamp anything outside the staging buffer
+        if (w0 < buf_saddr || w1 + 12 > buf_saddr + kBufBytes + 64) {
+            int* dbg = g_align_dbg;
+            const int slot = atomicAdd(dbg, 1);
+            if (slot < 6) {
+                int* d = dbg + 8 + slot * 8;
+                d[0] = (int)(w0 - buf_saddr); d[1] = pitch; d[2] = c0; d[3] = sy0; d[4] = X; d[5] = Y; d[6] = x0 * 1000 + yr0 * 10 + TH / 8; d[7] = lane * 100 + j;
             }
-            blend_tile_x<TH>(a, frame, tab, tm, buf_saddr0, (t % kTilesX) * kTileW, (t / kTilesX) * TH, lane,
-                             oblob, oal);
+            w0 = buf_saddr; w1 = buf_saddr;
+        }
+#endif
+        const unsigned shf = off << 3;                    // funnel shifts use the low 5 bits
+        const unsigned fx = (X >> 5) & 31, ty = Y & 0x3E0;
+        const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32_if3(w0 + 8, off, (unsigned)X);
+        const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32_if3(w1 + 8, off, (unsigned)Y);
+        blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
+                 __funnelshift_r(b1, b2, shf), fx, ty, vB[j], vG[j], vR[j]);
+    }
+    store_px<NJ>(o16 + (size_t)yb * kOut + x, o8 ? o8 + ((size_t)yb * kOut + x) * 3 : nullptr, vB, vG, vR);
+}
+
+// The same tile sampled tap by tap from global memory (boxes beyond the ladder, coordinates near
+// cv::remap's int16 saturation, frames that are not 16-byte aligned).  Rare: it runs in its own
+// kernel (align_direct_kernel) so the staged kernel carries no call, no stack and no extra
+// registers for it.  tab: adelta | bdelta of the crop, xy: (X0, Y0) of the band's 16 rows.
+template <int TH>
+__device__ __forceinline__ void blend_tile_direct(const AlignArgs& a, const uint8_t* frame, const int* tab,
+                                                  const int2* xy, int x0, int yr0, int lane, unsigned short* o16,
+                                                  uint8_t* o8) {
+    constexpr int NJ = TH / 2;
+    const int x = x0 + (lane & 15);
+    const int yb = yr0 + (lane >> 4);
+    const int ad = tab[x], bd = tab[kOut + x];
+    unsigned vB[NJ], vG[NJ], vR[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int2 p = xy[yb + 2 * j];
+        const int X = (p.x + ad) >> 5, Y = (p.y + bd) >> 5;
+        const int sx = max(-32768, min(32767, X >> 5));
+        const int sy = max(-32768, min(32767, Y >> 5));
+        const unsigned t00 = tap_global(a, frame, sx, sy), t01 = tap_global(a, frame, sx + 1, sy);
+        const unsigned t10 = tap_global(a, frame, sx, sy + 1), t11 = tap_global(a, frame, sx + 1, sy + 1);
+        blend_px(t00 | (t01 << 24), t01 >> 8, t10 | (t11 << 24), t11 >> 8, X & 31, (Y & 31) << 5, vB[j], vG[j],
+                 vR[j]);
+    }
+    store_px<NJ>(o16 + (size_t)yb * kOut + x, o8 ? o8 + ((size_t)yb * kOut + x) * 3 : nullptr, vB, vG, vR);
+}
+
+constexpr int kDirectWarps = 8;
+
+// one warp per (crop, band); returns at once unless the plan marked the crop direct
+__global__ void __launch_bounds__(kDirectWarps * 32) align_direct_kernel(const __grid_constant__ AlignArgs a) {
+    __shared__ int s_tab[kDirectWarps][2 * kOut];
+    __shared__ int2 s_xy[kDirectWarps][kBandRows];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kDirectWarps + warp;
+    if (item >= a.n * kBands) return;
+    const int crop = item / kBands, band = item % kBands;
+    const uint8_t* rec = a.rec + (size_t)crop * kRecBytes;
+    const CropHdr* h = reinterpret_cast<const CropHdr*>(rec);
+    if (!(h->flags & 1)) return;
+    const int* src = reinterpret_cast<const int*>(rec + 32);
+    for (int i = lane; i < 2 * kOut; i += 32) s_tab[warp][i] = src[i];
+    const int2* bxy = reinterpret_cast<const int2*>(rec + kCommonBytes + band * kBandBytes);
+    if (lane < kBandRows) s_xy[warp][lane] = bxy[lane];
+    __syncwarp();
+    const uint8_t* frame = a.frames + (size_t)h->frame * a.frame_bytes;
+    unsigned short* o16 = reinterpret_cast<unsigned short*>(a.out_blob) + (size_t)crop * 3 * kOut * kOut +
+                          (size_t)band * kBandRows * kOut;
+    uint8_t* o8 = a.out_aligned ? a.out_aligned + ((size_t)crop * kOut * kOut + (size_t)band * kBandRows * kOut) * 3
+                                : nullptr;
+    for (int t = 0; t < kTilesX; ++t)
+        blend_tile_direct<16>(a, frame, s_tab[warp], s_xy[warp], t * kTileW, 0, lane, o16, o8);
+}
+
+// all tiles of one band (16 output rows) of one crop with tile height TH
+template <int TH>
+__device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps, const CropHdr& h, uint32_t tabs,
+                                         uint32_t buf_saddr0, uint32_t bar_tile, uint32_t& parity, int lane,
+                                         unsigned short* o16, uint8_t* o8) {
+    constexpr int NT = kTilesX * (kBandRows / TH);       // 7 or 14 tiles
+    const uint32_t orgs = tabs + kCommonBytes + 128;     // (c0, sy0) per tile
+    if (h.flags & 1) return;          // direct crops are sampled by align_direct_kernel
+    const CUtensorMap* map = &maps.m[h.map];
+    const int pitch = h.pitch;
+    if (!(h.flags & 2)) {
+        // one buffer: the TMA latency of this warp is covered by the blends of the others
+        for (int t = 0; t < NT; ++t) {
+            const int2 org = lds64(orgs + 8 * t);
+            if (lane == 0) {
+                mbar_expect_tx_a(bar_tile, (uint32_t)h.box_bytes);
+                tma_load_3d(map, bar_tile, buf_saddr0, org.x, org.y, h.frame);
+            }
+            mbar_wait_a(bar_tile, parity & 1u);
+            parity ^= 1u;
+            blend_tile_staged<TH>(tabs, buf_saddr0, org.x, org.y, pitch, (t % kTilesX) * kTileW, (t / kTilesX) * TH,
+                                  lane, o16, o8);
             __syncwarp();
         }
         return;
     }
     // two half buffers: the next tile's box is in flight while this one is blended
-    TileMeta cur, nxt;
-    cur = stage_tile(pl, maps, tab, (t_begin % kTilesX) * kTileW, (t_begin / kTilesX) * TH, fi, buf_saddr0,
-                     &bars[0], lane);
-    nxt = cur;
-    for (int t = t_begin; t < t_end; ++t) {
-        const int b = (t - t_begin) & 1;
-        if (t + 1 < t_end) {
-            const int tn = t + 1;
-            nxt = stage_tile(pl, maps, tab, (tn % kTilesX) * kTileW, (tn / kTilesX) * TH, fi,
-                             buf_saddr0 + (uint32_t)((b ^ 1) * kHalfBuf), &bars[b ^ 1], lane);
+    int2 cur = lds64(orgs);
+    if (lane == 0) {
+        mbar_expect_tx_a(bar_tile, (uint32_t)h.box_bytes);
+        tma_load_3d(map, bar_tile, buf_saddr0, cur.x, cur.y, h.frame);
+    }
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+        const int b = t & 1;
+        int2 nxt = cur;
+        if (t + 1 < NT) {
+            nxt = lds64(orgs + 8 * (t + 1));
+            if (lane == 0) {
+                mbar_expect_tx_a(bar_tile + 8 * (b ^ 1), (uint32_t)h.box_bytes);
+                tma_load_3d(map, bar_tile + 8 * (b ^ 1), buf_saddr0 + (uint32_t)((b ^ 1) * kHalfBuf), nxt.x, nxt.y,
+                            h.frame);
+            }
         }
-        mbar_wait(&bars[b], (parity >> b) & 1u);
+        mbar_wait_a(bar_tile + 8 * b, (parity >> b) & 1u);
         parity ^= (1u << b);
-        blend_tile_x<TH>(a, frame, tab, cur, buf_saddr0 + (uint32_t)(b * kHalfBuf), (t % kTilesX) * kTileW,
-                         (t / kTilesX) * TH, lane, oblob, oal);
+        blend_tile_staged<TH>(tabs, buf_saddr0 + (uint32_t)(b * kHalfBuf), cur.x, cur.y, pitch,
+                              (t % kTilesX) * kTileW, (t / kTilesX) * TH, lane, o16, o8);
         __syncwarp();      // every lane is done with buffer b before it is refilled
         cur = nxt;
     }
 }
 
-// One thread per crop: forward similarity (or the caller's matrix), cv2's inverse, and the
-// degenerate-matrix guard.  Runs ahead of align_kernel so that the work items of a crop do
-// not each repeat the fp64 estimate.
-__global__ void align_plan_kernel(const AlignArgs a) {
-    const int crop = blockIdx.x * blockDim.x + threadIdx.x;
-    if (crop >= a.n) return;
-    double M[6], iM[6];
-    if (a.M) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) M[i] = a.M[(size_t)crop * 6 + i];
-    } else {
-        float lm[10];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) lm[i] = a.lmk[(size_t)crop * 10 + i];
-        estimate_norm_dev(lm, M);
-    }
-    invert_affine_dev(M, iM);
-    bool finite = true;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) finite = finite && (fabs(iM[i]) < 1e12);
-    if (!finite) { iM[0] = iM[1] = iM[3] = iM[4] = 0.0; iM[2] = iM[5] = -1e6; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) a.iM[(size_t)crop * 6 + i] = iM[i];
-}
-
+// One warp per work item = (crop, band of 16 output rows), handed out by a dynamic counter two
+// tickets ahead: while item i is blended, the plan record of item i+1 is already landing in the
+// other table slot (two bulk copies: the crop's common block and the band block).
 __global__ void __launch_bounds__(kWarps * 32, 1)
-align_kernel(const __grid_constant__ TmapSet maps, const AlignArgs a) {
+align_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ AlignArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint8_t* wsm = smem + (size_t)warp * kWarpSmem;
-    int* tab = reinterpret_cast<int*>(wsm);
-    const uint32_t buf_saddr0 = smem_u32(wsm + kTabBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kTabBytes + kBufBytes);
+    const uint32_t wsm = ((smem_u32(smem_raw) + 127u) & ~127u) + (uint32_t)warp * kWarpSmem;
+    const uint32_t tab0 = wsm;                              // two table slots of kItemBytes
+    const uint32_t buf_al = wsm + kTabBytes;                // staging buffer (128-byte aligned)
+    // [0,1] tile barriers, [2,3] item barriers.  64 bytes of slack separate them from the staging
+    // buffer: the tap loads of a box that ends at the end of the buffer read up to 11 bytes
+    // past it (never selected), and plain loads must not touch mbarrier objects
+    const uint32_t bars = wsm + kTabBytes + kBufBytes + 64;
     if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * i));
         mbar_fence_init();
     }
-    __syncthreads();
-    uint32_t parity = 0;
+    __syncwarp();
+    uint32_t parity = 0;        // bits 0,1 tile barriers; bits 2,3 item barriers
 
-    const int nitems = a.n * kItemsPerCrop;
-    // the counter is bumped one item ahead: the atomic's round trip overlaps the current item
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(a.counter, 1);
-    for (;;) {
-        const int item = __shfl_sync(FRP_FULL_MASK, ticket, 0);
-        if (item >= nitems) break;
-        if (lane == 0) ticket = atomicAdd(a.counter, 1);
-        const int crop = item / kItemsPerCrop;
-        const int half = item % kItemsPerCrop;
-
-        // ---- inverse map of this crop (align_plan_kernel computed it once per crop) ----
-        double iM[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) iM[i] = a.iM[(size_t)crop * 6 + i];
-        int fi = a.frame_idx[crop];
-        fi = min(max(fi, 0), a.F - 1);
-        const uint8_t* frame = a.frames + (size_t)fi * a.frame_bytes;
-        __syncwarp();
-        for (int x = lane; x < kOut; x += 32) {
-            const double xd = (double)x;
-            tab[x] = __double2int_rn(__dmul_rn(__dmul_rn(iM[0], xd), 1024.0));
-            tab[kOut + x] = __double2int_rn(__dmul_rn(__dmul_rn(iM[3], xd), 1024.0));
-            // (X0[y], Y0[y]) interleaved: the blend fetches both with one 64-bit load
-            tab[2 * kOut + 2 * x] =
-                __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[1], xd), iM[2]), 1024.0)) + 16;
-            tab[2 * kOut + 2 * x + 1] =
-                __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[4], xd), iM[5]), 1024.0)) + 16;
+    const int nitems = a.n * kBands;
+    auto issue_item = [&](int item, int slot) {
+        const uint8_t* rec = a.rec + (size_t)(item / kBands) * kRecBytes;
+        const uint32_t bar = bars + 16 + 8 * slot;
+        const uint32_t dst = tab0 + (uint32_t)slot * kItemBytes;
+        mbar_expect_tx_a(bar, kItemBytes);
+        bulk_g2s_a(dst, rec, kCommonBytes, bar);
+        bulk_g2s_a(dst + kCommonBytes, rec + kCommonBytes + (item % kBands) * kBandBytes, kBandBytes, bar);
+    };
+    int t_cur = 0, t_next = 0;
+    if (lane == 0) {
+        t_cur = atomicAdd(a.counter, 1);
+        t_next = atomicAdd(a.counter, 1);
+        if (t_cur < nitems) issue_item(t_cur, 0);
+    }
+    t_cur = __shfl_sync(FRP_FULL_MASK, t_cur, 0);
+    t_next = __shfl_sync(FRP_FULL_MASK, t_next, 0);
+    int slot = 0;
+    while (t_cur < nitems) {
+        int t_next2 = 0;
+        if (lane == 0) {
+            if (t_next < nitems) issue_item(t_next, slot ^ 1);     // the other slot's item is finished
+            t_next2 = atomicAdd(a.counter, 1);                   // round trip overlaps this item
         }
-        __syncwarp();
-
-        __half* oblob = a.out_blob + (size_t)crop * 3 * kOut * kOut;
-        uint8_t* oal = a.out_aligned ? a.out_aligned + (size_t)crop * kOut * kOut * 3 : nullptr;
-
-        // ---- staging plan: tile height, box size, single or double buffering ----
-        const double ax = fabs(iM[0]), ay = fabs(iM[1]), bx = fabs(iM[3]), by = fabs(iM[4]);
-        int wi16 = 0, hi16 = 0, wi8 = 0, hi8 = 0;
-        const bool fit16 = plan_box<16>(ax, ay, bx, by, wi16, hi16);
-        const bool fit8 = plan_box<8>(ax, ay, bx, by, wi8, hi8);
-        const int bytes16 = c_box_w[wi16] * c_box_h[hi16], bytes8 = c_box_w[wi8] * c_box_h[hi8];
-        // coordinates near the int16 saturation of cv::remap's xy map are handled tap by tap:
-        // the map is affine, so its extremes over the crop are at the four corners
-        bool far = false;
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-            for (int cx = 0; cx < 2; ++cx) {
-                const double sx = iM[0] * (cx * (kOut - 1)) + iM[1] * (cy * (kOut - 1)) + iM[2];
-                const double sy = iM[3] * (cx * (kOut - 1)) + iM[4] * (cy * (kOut - 1)) + iM[5];
-                far = far || !(fabs(sx) < 29000.0 && fabs(sy) < 29000.0);
-            }
-        const bool tma_ok = a.use_tma && !far;
-        bool th16;
-        CropPlan pl;
-        if (FRP_ALIGN_PREF == 0)
-            th16 = fit16 && (bytes16 <= kHalfBuf || !(fit8 && bytes8 <= kHalfBuf));
-        else
-            th16 = fit16;
-        pl.direct = !(tma_ok && (th16 ? fit16 : fit8));
-        const int wi = th16 ? wi16 : wi8, hi = th16 ? hi16 : hi8;
-        const int th1 = th16 ? 15 : 7;
-        pl.map = hi * kNumW + wi;
-        pl.pitch = c_box_w[wi];
-        pl.box_bytes = th16 ? bytes16 : bytes8;
-        pl.dual = !pl.direct && pl.box_bytes <= kHalfBuf;
-        pl.xsel_x = (iM[0] >= 0.0) ? 0 : kTileW - 1;
-        pl.ysel_x = (iM[1] >= 0.0) ? 0 : th1;
-        pl.xsel_y = (iM[3] >= 0.0) ? 0 : kTileW - 1;
-        pl.ysel_y = (iM[4] >= 0.0) ? 0 : th1;
-        if (th16) {
-            const int nt = kTilesX * (kOut / 16);   // 49
-            run_tiles<16>(a, maps, pl, frame, fi, tab, buf_saddr0, bars, parity, half * nt / kItemsPerCrop,
-                          (half + 1) * nt / kItemsPerCrop, lane, oblob, oal);
-        } else {
-            const int nt = kTilesX * (kOut / 8);    // 98
-            run_tiles<8>(a, maps, pl, frame, fi, tab, buf_saddr0, bars, parity, half * nt / kItemsPerCrop,
-                         (half + 1) * nt / kItemsPerCrop, lane, oblob, oal);
+        const uint32_t tabs = tab0 + (uint32_t)slot * kItemBytes;
+        mbar_wait_a(bars + 16 + 8 * slot, (parity >> (2 + slot)) & 1u);
+        parity ^= (4u << slot);
+        CropHdr h;
+        {
+            const int2 h0 = lds64(tabs), h1 = lds64(tabs + 8);
+            h.frame = h0.x; h.map = h0.y; h.pitch = h1.x; h.box_bytes = h1.y; h.flags = (int)lds32(tabs + 16);
         }
+        const int crop = t_cur / kBands, band = t_cur % kBands;
+        unsigned short* o16 = reinterpret_cast<unsigned short*>(a.out_blob) + (size_t)crop * 3 * kOut * kOut +
+                              (size_t)band * kBandRows * kOut;
+        uint8_t* o8 = a.out_aligned ? a.out_aligned + ((size_t)crop * kOut * kOut + (size_t)band * kBandRows * kOut) * 3
+                                    : nullptr;
+        if (h.flags & 4) run_band<8>(a, maps, h, tabs, buf_al, bars, parity, lane, o16, o8);
+        else run_band<16>(a, maps, h, tabs, buf_al, bars, parity, lane, o16, o8);
+        __syncwarp();
+        t_cur = t_next;
+        t_next = __shfl_sync(FRP_FULL_MASK, t_next2, 0);
+        slot ^= 1;
     }
 }
 
@@ -478,9 +610,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// u8 tensor [F][H][3W bytes] with pitches (stride, frame_bytes); one map per box size
-bool encode_frame_maps(TmapSet* set, const uint8_t* frames, int F, int H, int W, size_t stride,
-                       size_t frame_bytes) {
+// u8 tensor [F][H][3W bytes] with pitches (stride, frame_bytes); one map per box size.  The 66
+// descriptors of a frame buffer are cached per thread (encoding them costs ~30 us): a camera
+// pipeline passes the same device buffer tick after tick.
+struct MapCache {
+    const uint8_t* frames = nullptr;
+    int F = 0, H = 0, W = 0;
+    size_t stride = 0;
+    bool ok = false;
+    TmapSet set;
+};
+
+bool encode_frame_maps(MapCache* mc, const uint8_t* frames, int F, int H, int W, size_t stride, size_t frame_bytes) {
+    if (mc->frames == frames && mc->F == F && mc->H == H && mc->W == W && mc->stride == stride) return mc->ok;
+    mc->frames = frames; mc->F = F; mc->H = H; mc->W = W; mc->stride = stride; mc->ok = false;
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tensormap_encode_fn());
     if (!fn) return false;
     if (((uintptr_t)frames & 15) || (stride & 15) || (frame_bytes & 15)) return false;
@@ -489,12 +632,13 @@ bool encode_frame_maps(TmapSet* set, const uint8_t* frames, int F, int H, int W,
     cuuint32_t estr[3] = {1, 1, 1};
     for (int hi = 0; hi < kNumH; ++hi)
         for (int wi = 0; wi < kNumW; ++wi) {
-            cuuint32_t box[3] = {(cuuint32_t)kHostBoxW[wi], (cuuint32_t)kHostBoxH[hi], 1};
-            CUresult r = fn(&set->m[hi * kNumW + wi], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(frames),
+            cuuint32_t box[3] = {(cuuint32_t)box_w(wi), (cuuint32_t)box_h(hi), 1};
+            CUresult r = fn(&mc->set.m[hi * kNumW + wi], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(frames),
                             gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return false;
         }
+    mc->ok = true;
     return true;
 }
 
@@ -521,9 +665,9 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
         return FRP_E_NODEVICE;
     }
     const bool prof = g_align_profile.load(std::memory_order_relaxed) != 0;
-    // workspace: the work counter (first 256 bytes) and the per-crop inverse maps
+    // workspace: the work counter (first 256 bytes) and the per-crop plan records
     uint8_t* ws = nullptr;
-    FRP_CUDA(cudaMallocAsync((void**)&ws, 256 + (size_t)n * 6 * sizeof(double), st));
+    FRP_CUDA(cudaMallocAsync((void**)&ws, 256 + (size_t)n * kRecBytes, st));
     int* counter = reinterpret_cast<int*>(ws);
     FRP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     AlignArgs a;
@@ -533,27 +677,45 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     a.out_blob = reinterpret_cast<__half*>(out_blob);
     a.out_aligned = out_aligned;
     a.counter = counter;
-    a.iM = reinterpret_cast<double*>(ws + 256);
-    TmapSet maps;
-    memset(&maps, 0, sizeof(maps));
-    a.use_tma = encode_frame_maps(&maps, frames, F, H, W, stride, a.frame_bytes) ? 1 : 0;
+    a.rec = ws + 256;
+    static thread_local MapCache mc;
+    if (!encode_frame_maps(&mc, frames, F, H, W, stride, a.frame_bytes)) memset(&mc.set, 0, sizeof(mc.set));
+    a.use_tma = mc.ok ? 1 : 0;
     const size_t smem = (size_t)kWarps * kWarpSmem + 128;
     {
         int rc = FRP_OK;
         configure_func_smem((const void*)align_kernel, device, smem, &rc);
         if (rc) return rc;
     }
-    const int items = n * kItemsPerCrop;
+    const int items = n * kBands;
     int grid = (items + kWarps - 1) / kWarps;
     if (grid > s_sms[di]) grid = s_sms[di];
     if (prof) {
         if (!t_align_ev[0]) { cudaEventCreate(&t_align_ev[0]); cudaEventCreate(&t_align_ev[1]); }
         cudaEventRecord(t_align_ev[0], st);
     }
-    align_plan_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+    align_plan_kernel<<<(n + kPlanWarps - 1) / kPlanWarps, kPlanWarps * 32, 0, st>>>(a);
     FRP_CHECK_LAUNCH();
-    align_kernel<<<grid, kWarps * 32, smem, st>>>(maps, a);
+    align_kernel<<<grid, kWarps * 32, smem, st>>>(mc.set, a);
     FRP_CHECK_LAUNCH();
+    align_direct_kernel<<<(items + kDirectWarps - 1) / kDirectWarps, kDirectWarps * 32, 0, st>>>(a);
+    FRP_CHECK_LAUNCH();
+#ifdef FRP_ALIGN_DEBUG
+    {
+        int h_dbg[64];
+        cudaError_t de = cudaStreamSynchronize(st);
+        fprintf(stderr, "[align debug] sync: %s\n", cudaGetErrorString(de));
+        if (cudaMemcpyFromSymbol(h_dbg, g_align_dbg, sizeof(h_dbg)) == cudaSuccess) {
+            fprintf(stderr, "[align debug] out-of-buffer tap addresses: %d\n", h_dbg[0]);
+            for (int i = 0; i < 6 && i < h_dbg[0]; ++i) {
+                const int* d = h_dbg + 8 + i * 8;
+                fprintf(stderr, "  rel=%d pitch=%d c0=%d sy0=%d X=%d Y=%d tile=%d lane_j=%d\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+            }
+            memset(h_dbg, 0, sizeof(h_dbg));
+            cudaMemcpyToSymbol(g_align_dbg, h_dbg, sizeof(h_dbg));
+        }
+    }
+#endif
     if (prof) { cudaEventRecord(t_align_ev[1], st); t_align_valid = true; }
     FRP_CUDA(cudaFreeAsync(ws, st));
     return FRP_OK;

@@ -182,7 +182,7 @@ def test_device_path_many_crops():
     before = frp_b200.kernel_launches()
     align.norm_crop_batch_device(d_fr, F, H, W, 3 * W, d_fi, d_lm, n, out, out_al, stream=st)
     torch.cuda.synchronize()
-    assert frp_b200.kernel_launches() == before + 2      # align_plan_kernel + align_kernel
+    assert frp_b200.kernel_launches() == before + 3      # align_plan_kernel + align_kernel + align_direct_kernel
     al = out_al.cpu().numpy()
     blob = out.cpu().numpy()
     sel = np.random.default_rng(0).choice(n, 64, replace=False)
