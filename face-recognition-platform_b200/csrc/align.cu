@@ -98,7 +98,8 @@ struct AlignArgs {
     int n;
     __half* out_blob;     // [n][3][112][112]
     uint8_t* out_aligned; // [n][112][112][3] or null
-    int* counter;         // dynamic work counter
+    int* counter;         // [0] dynamic work counter, [1] number of direct crops
+    int* direct_list;     // [n] crops the plan marked direct (compact, unordered)
     uint8_t* rec;         // [n][kRecBytes] plan records (workspace, written by align_plan_kernel)
     int use_tma;          // tensor maps valid (16-byte aligned base / pitch)
 };
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __gri
         h.flags = (direct ? 1 : 0) | (dual ? 2 : 0) | (th16 ? 0 : 4);
         h.pad[0] = h.pad[1] = h.pad[2] = 0;
         *reinterpret_cast<CropHdr*>(rec) = h;
+        if (direct) a.direct_list[atomicAdd(a.counter + 1, 1)] = crop;
     }
     // ---- source origin of every tile: the map is affine and the tables are monotone, so the
     // minimum corner of a tile's footprint is the sum of two table entries whose positions
@@ -450,18 +452,21 @@ __device__ __forceinline__ void blend_tile_direct(const AlignArgs& a, const uint
 
 constexpr int kDirectWarps = 8;
 
-// one warp per (crop, band); returns at once unless the plan marked the crop direct
+// one warp per (direct crop, band), over the compact list the plan kernel wrote: a small fixed
+// grid that exits at once when no crop needs it (the usual case)
+constexpr int kDirectBlocks = 64;
+
 __global__ void __launch_bounds__(kDirectWarps * 32) align_direct_kernel(const __grid_constant__ AlignArgs a) {
     __shared__ int s_tab[kDirectWarps][2 * kOut];
     __shared__ int2 s_xy[kDirectWarps][kBandRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * kDirectWarps + warp;
-    if (item >= a.n * kBands) return;
-    const int crop = item / kBands, band = item % kBands;
+    const int nitems = a.counter[1] * kBands;
+    for (int item = blockIdx.x * kDirectWarps + warp; item < nitems; item += gridDim.x * kDirectWarps) {
+    const int crop = a.direct_list[item / kBands], band = item % kBands;
     const uint8_t* rec = a.rec + (size_t)crop * kRecBytes;
     const CropHdr* h = reinterpret_cast<const CropHdr*>(rec);
-    if (!(h->flags & 1)) return;
     const int* src = reinterpret_cast<const int*>(rec + 32);
+    __syncwarp();
     for (int i = lane; i < 2 * kOut; i += 32) s_tab[warp][i] = src[i];
     const int2* bxy = reinterpret_cast<const int2*>(rec + kCommonBytes + band * kBandBytes);
     if (lane < kBandRows) s_xy[warp][lane] = bxy[lane];
@@ -473,6 +478,7 @@ __global__ void __launch_bounds__(kDirectWarps * 32) align_direct_kernel(const _
                                 : nullptr;
     for (int t = 0; t < kTilesX; ++t)
         blend_tile_direct<16>(a, frame, s_tab[warp], s_xy[warp], t * kTileW, 0, lane, o16, o8);
+    }
 }
 
 // all tiles of one band (16 output rows) of one crop with tile height TH
@@ -667,9 +673,10 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     const bool prof = g_align_profile.load(std::memory_order_relaxed) != 0;
     // workspace: the work counter (first 256 bytes) and the per-crop plan records
     uint8_t* ws = nullptr;
-    FRP_CUDA(cudaMallocAsync((void**)&ws, 256 + (size_t)n * kRecBytes, st));
+    const size_t list_bytes = (((size_t)n * sizeof(int)) + 255) & ~(size_t)255;
+    FRP_CUDA(cudaMallocAsync((void**)&ws, 256 + list_bytes + (size_t)n * kRecBytes, st));
     int* counter = reinterpret_cast<int*>(ws);
-    FRP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    FRP_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
     AlignArgs a;
     a.frames = frames; a.F = F; a.H = H; a.W = W; a.stride = stride;
     a.frame_bytes = (size_t)H * stride;
@@ -677,7 +684,8 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     a.out_blob = reinterpret_cast<__half*>(out_blob);
     a.out_aligned = out_aligned;
     a.counter = counter;
-    a.rec = ws + 256;
+    a.direct_list = reinterpret_cast<int*>(ws + 256);
+    a.rec = ws + 256 + list_bytes;
     static thread_local MapCache mc;
     if (!encode_frame_maps(&mc, frames, F, H, W, stride, a.frame_bytes)) memset(&mc.set, 0, sizeof(mc.set));
     a.use_tma = mc.ok ? 1 : 0;
@@ -698,7 +706,7 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     FRP_CHECK_LAUNCH();
     align_kernel<<<grid, kWarps * 32, smem, st>>>(mc.set, a);
     FRP_CHECK_LAUNCH();
-    align_direct_kernel<<<(items + kDirectWarps - 1) / kDirectWarps, kDirectWarps * 32, 0, st>>>(a);
+    align_direct_kernel<<<kDirectBlocks, kDirectWarps * 32, 0, st>>>(a);
     FRP_CHECK_LAUNCH();
 #ifdef FRP_ALIGN_DEBUG
     {

@@ -126,7 +126,9 @@ bool gemm_supported(const frp_gallery* g);
 int gemm_num_lists(const frp_gallery* g, int B);
 // tmap_q: the caller's cached descriptor of q16 ([groups*128][dimp] fp16), see Workspace
 int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int B, int KP,
-                      uint64_t* cand, int nlists, cudaStream_t st);
+                      uint64_t* cand, int nlists, cudaStream_t st, uint64_t rows_limit = 0);
+// pure top-k: raise every query's prefilter cut to (k-th best key of `cand`) - 2 eps
+int launch_raise_cut(QParams* qp, int B, int k, const uint64_t* cand, int nlists, int KP, cudaStream_t st);
 int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp);
 
 // (re)encode the gallery's cached tensor maps; caller holds the unique lock (or owns g exclusively)

@@ -176,7 +176,15 @@ int match_device_locked(frp_gallery* g, const float* q_dev, size_t qstride, cons
     if (ev) cudaEventRecord(ev[1], st);
     if (!rc) {
         if (use_gemm) {
-            rc = launch_match_gemm(g, w->tmap_q, qp, B, KP, cand, nlists, st);
+            // pure top-k over a large gallery: a sampling pass over the first ~1.5 % of the rows
+            // lifts every query's cut from -inf to a sound bound (see raise_cut_kernel), so the
+            // main pass inserts a handful of candidates per list instead of ~KP ln(rows / KP)
+            const uint64_t sample = (uint64_t)nlists * 4 * 256;
+            if ((flags & FRP_MATCH_NO_THRESHOLD) && !(flags & FRP_MATCH_NO_SAMPLE) && g->rows >= 32 * sample) {
+                rc = launch_match_gemm(g, w->tmap_q, qp, B, KP, cand, nlists, st, sample);
+                if (!rc) rc = launch_raise_cut(qp, B, k, cand, nlists, KP, st);
+            }
+            if (!rc) rc = launch_match_gemm(g, w->tmap_q, qp, B, KP, cand, nlists, st);
             set_match_path("gemm_tcgen05");
         } else {
             rc = launch_match_scan(g, exact, qprep, qp, B, KP, cand, nlists, st);

@@ -714,7 +714,9 @@ int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp) {
 }
 
 int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int B, int KP, uint64_t* cand,
-                      int nlists, cudaStream_t st) {
+                      int nlists, cudaStream_t st, uint64_t rows_limit) {
+    // rows_limit > 0: scan only the first rows_limit rows (the sampling pass of pure top-k)
+    const uint64_t rows = (rows_limit && rows_limit < g->rows) ? rows_limit : g->rows;
     const int groups = gemm_groups(B);
     const int nkb = g->dimp / kBlockK;
     const bool l2 = (g->metric == FRP_METRIC_L2);
@@ -732,8 +734,8 @@ int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int
     a.norm2 = g->norm2;
     a.qp = qp;
     a.cand = cand;
-    a.rows = (uint32_t)g->rows;
-    a.ntiles = (uint32_t)((g->rows + kTileN - 1) / kTileN);
+    a.rows = (uint32_t)rows;
+    a.ntiles = (uint32_t)((rows + kTileN - 1) / kTileN);
     a.B = B;
     a.nkb = nkb;
     a.stages = stages;

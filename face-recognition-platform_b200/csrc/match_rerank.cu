@@ -284,6 +284,60 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs
 }
 
 // ---------------------------------------------------------------------------
+// raise_cut: pure top-k (no threshold) keeps a live top-KP per prefilter thread, and the insert
+// rate of a list that starts from -inf only decays like KP/rows_seen.  A sampling pass over the
+// first ~1.5 % of the gallery gives every query k real candidates; every row of the final top-k
+// must score at least as well as the k-th of them, so the main pass can run thresholded at
+//     cut = (k-th best approximate score of the sample) - 2 eps
+// (a row of the true top-k has exact score >= the exact score of that sample row >= its
+// approximate score - eps, and its own approximate score is within eps of the exact one).
+// One block per query: compact the sample's keys, find the k-th largest, lift cut0.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raise_cut_kernel(QParams* __restrict__ qp, int k,
+                                                        const uint64_t* __restrict__ cand, int total) {
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_prefix, s_need;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const uint64_t* c = cand + (size_t)b * total;
+    // radix select on the 32-bit orderable score (4 passes of 8 bits, most significant first):
+    // the k-th largest key's score without sorting the ~5 000 keys
+    unsigned int prefix = 0, need = (unsigned int)k;
+    bool enough = true;
+    for (int pass = 0; pass < 4 && enough; ++pass) {
+        const int shift = 24 - 8 * pass;
+        s_hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += blockDim.x) {
+            const uint64_t key = c[i];
+            if (!key) continue;
+            const unsigned int o = (unsigned int)(key >> 32);
+            if (pass == 0 || (o >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(o >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int acc = 0;
+            int d = 255;
+            for (; d >= 0; --d) {
+                if (acc + s_hist[d] >= need) break;
+                acc += s_hist[d];
+            }
+            if (d < 0) { s_need = 0xffffffffu; }              // fewer than k keys in the sample
+            else { s_prefix = prefix | ((unsigned int)d << shift); s_need = need - acc; }
+        }
+        __syncthreads();
+        if (s_need == 0xffffffffu) enough = false;
+        else { prefix = s_prefix; need = s_need; }
+        __syncthreads();
+    }
+    if (tid == 0 && enough) {
+        QParams p = qp[b];
+        const float kth = f32_from_orderable(prefix);
+        const float lifted = __fadd_rd(kth, -2.f * p.eps);
+        if (lifted == lifted && lifted > p.cut0) { p.cut0 = lifted; qp[b] = p; }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // dense scores: one warp per gallery row, fp64 from the fp32 master.
 // ---------------------------------------------------------------------------
 __global__ void scores_kernel(const float* __restrict__ g32, const uint8_t* __restrict__ alive,
@@ -519,6 +573,12 @@ int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride
                         QParams* qp, cudaStream_t st) {
     prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, qstride, q_rows, g->dim, g->dimp, g->metric, tau, flags,
                                            eps_mode, g->gmax, g->gerr, qprep, q16, qp);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+int launch_raise_cut(QParams* qp, int B, int k, const uint64_t* cand, int nlists, int KP, cudaStream_t st) {
+    raise_cut_kernel<<<B, 256, 0, st>>>(qp, k, cand, nlists * KP);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }

@@ -19,6 +19,7 @@ METRIC_L2, METRIC_COS = 0, 1
 MATCH_THRESHOLD, MATCH_NO_THRESHOLD, MATCH_FORCE_SCAN, MATCH_FORCE_GEMM, MATCH_FORCE_EXACT, MATCH_STRICT = \
     0x0, 0x1, 0x2, 0x4, 0x8, 0x10
 MATCH_WIDE = 0x20
+MATCH_NO_SAMPLE = 0x40
 STATUS_OK, STATUS_FALLBACK, STATUS_UNCERTIFIED = 0, 1, 2
 
 

@@ -55,6 +55,7 @@ extern "C" {
 #define FRP_MATCH_FORCE_EXACT 0x8  /* scan the fp32 master instead of the fp16 copy */
 #define FRP_MATCH_STRICT      0x10 /* strict comparison (d < tau): store_face duplicate check, face_service.py:360 */
 #define FRP_MATCH_WIDE        0x20 /* frp_match_device: widest candidate lists (64 per CTA); second-level fallback */
+#define FRP_MATCH_NO_SAMPLE   0x40 /* pure top-k: skip the sampling pass that lifts the prefilter cut (A/B measurements) */
 
 /* per-query status written by frp_match */
 #define FRP_STATUS_OK        0  /* result certified exact w.r.t. the fp32 master */

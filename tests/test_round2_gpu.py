@@ -134,6 +134,36 @@ def test_large_topk_runs_on_the_tensor_cores(metric, k):
         g.close()
 
 
+def test_pure_topk_sampling_pass_is_sound():
+    """find_k_nearest semantics at scale: the sampling pass that lifts the prefilter cut (first
+    ~1.5 % of the rows) must never lose a true neighbour — same answer as the oracle and as the
+    run without sampling, including queries whose best rows sit in the LAST rows and heavy ties."""
+    from frp_b200._capi import MATCH_NO_SAMPLE
+    N = 3_000_000
+    G = o.synth_l2_gallery(N, 128, seed=71).astype(np.float32)
+    G[N - 40_000:N - 20_000:1000] = G[123]     # 21 exact copies far from the sampled prefix, in different tiles
+    Q, planted = o.synth_l2_queries(G, 48, seed=72)
+    Q = Q.astype(np.float32)
+    Q[0] = G[123]
+    Q[1] = G[N - 1]
+    g = Gallery(128, METRIC_L2, capacity=N)
+    g.append(G)
+    try:
+        for k in (5, 10, 50):
+            want = o.l2_match_topk_fast(G, Q, 0.0, k, False)
+            a = g.match(Q, 0.0, k, MATCH_NO_THRESHOLD)
+            b = g.match(Q, 0.0, k, MATCH_NO_THRESHOLD | MATCH_NO_SAMPLE)
+            assert np.all(a[3] <= 1) and np.all(b[3] <= 1)
+            assert (a[3] == 0).sum() >= len(Q) - 2          # certified on the tcgen05 route, sampling included
+            g.match(Q[2:], 0.0, k, MATCH_NO_THRESHOLD)
+            assert frp_b200.last_match_path() == "gemm_tcgen05"
+            _assert_topk_equal(a[0], a[1], a[2], *want, ("sampled", k))
+            _assert_topk_equal(b[0], b[1], b[2], *want, ("unsampled", k))
+        assert a[0][0, :21].tolist() == [123] + list(range(N - 40_000, N - 20_000, 1000))
+    finally:
+        g.close()
+
+
 def test_face_service_batches_use_the_tensor_cores_and_check_status():
     """batch_compare_faces / scan_cameras ask for 64 results per query; that must not fall back
     to passes of the scan kernel (advisor finding), and an uncertifiable tie block (> 64 exact
