@@ -673,8 +673,14 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     const bool prof = g_align_profile.load(std::memory_order_relaxed) != 0;
     // workspace: the work counter (first 256 bytes) and the per-crop plan records
     uint8_t* ws = nullptr;
+    // persistent per-(thread, stream) block: the steady state of a camera pipeline allocates nothing
     const size_t list_bytes = (((size_t)n * sizeof(int)) + 255) & ~(size_t)255;
-    FRP_CUDA(cudaMallocAsync((void**)&ws, 256 + list_bytes + (size_t)n * kRecBytes, st));
+    Workspace* wsp = workspace_for(device, st);
+    {
+        const int rc = workspace_reserve(wsp, 256 + list_bytes + (size_t)n * kRecBytes, 0);
+        if (rc) return rc;
+    }
+    ws = wsp->dev;
     int* counter = reinterpret_cast<int*>(ws);
     FRP_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
     AlignArgs a;
@@ -725,7 +731,6 @@ int align_device_impl(int device, const uint8_t* frames, int F, int H, int W, si
     }
 #endif
     if (prof) { cudaEventRecord(t_align_ev[1], st); t_align_valid = true; }
-    FRP_CUDA(cudaFreeAsync(ws, st));
     return FRP_OK;
 }
 

@@ -465,7 +465,21 @@ int frp_scores(frp_gallery_t* g, const float* queries, int B, double* out, uint6
     if (rows == 0) return FRP_OK;
     DeviceGuard dg(g->device);
     cudaStream_t st = thread_stream(g->device);
-    // dense dumps are large (B x rows doubles): a call-scoped stream-ordered allocation, not workspace
+    // dense dumps are large (B x rows doubles): a call-scoped stream-ordered allocation, not
+    // workspace; the pool keeps freed blocks so repeated calls do not go back to the driver
+    {
+        static std::once_flag once[16];
+        const int dv = g->device;
+        if (dv >= 0 && dv < 16)
+            std::call_once(once[dv], [dv]() {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dv) == cudaSuccess) {
+                    uint64_t thr = ~0ull;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+                }
+                cudaGetLastError();
+            });
+    }
     float* dq = nullptr; double* dout = nullptr;
     FRP_CUDA(cudaMallocAsync((void**)&dq, (size_t)B * g->dim * sizeof(float), st));
     cudaError_t e = cudaMallocAsync((void**)&dout, (size_t)B * rows * sizeof(double), st);
