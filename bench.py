@@ -49,8 +49,9 @@ def parse():
     ap.add_argument("--exchange", default=os.environ.get("FRP_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
                     help="multi-GPU merge: NCCL all-gather + merge kernel, or the fused peer-memory kernel")
     ap.add_argument("--also-batches", default="", help="comma list of extra batch sizes timed on the same gallery")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="run all-gather + merge on the step's own stream instead of the two-slot pipeline")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="two-slot pipeline (all-gather + merge of step i behind the prefilter of step i+1) instead of the CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of one CUDA graph per step")
     ap.add_argument("--c3", choices=["auto", "on", "off"], default="auto",
                     help="100 M-row leg (12.5 M rows per rank): auto = when 8 ranks run")
     return ap.parse_args()
@@ -393,12 +394,33 @@ def run_ours(args):
     def step(i):
         return matcher.match(queries[i], tau, k)
 
-    pipelined = (args.exchange == "nccl") and not args.no_pipeline
+    # default stepping: one CUDA graph per step (prep -> tcgen05 prefilter -> re-rank -> all-gather
+    # -> merge are 5-6 dependent launches; their gaps are ~15 % of a 0.29 ms step at 8 ranks).
+    # --pipeline: two-slot pipeline over two streams instead; --no-graph: plain launches.
+    pipelined = args.pipeline and args.exchange == "nccl"
+    graph = None
+    launches_per_graph_step = 0
+    if not args.no_graph and not pipelined and args.exchange == "nccl":
+        try:
+            q_static = queries[0].clone()
+            l0 = frp.kernel_launches()
+            graph, g_out = matcher.capture(q_static, tau, k)
+            # capture() issues the step three times (two warm-ups + the captured one); a replay
+            # launches the same kernels without passing through the library's launch counter
+            launches_per_graph_step = (frp.kernel_launches() - l0) // 3
+        except Exception as e:      # pragma: no cover - a capture failure must not lose the run
+            sys.stderr.write("CUDA graph capture failed (%r): plain launches\n" % (e,))
+            graph = None
 
     def run_steps(a, b):
         """Steps a..b-1.  Pipelined (default): the all-gather + merge of step i run on the
         exchange stream behind the prefilter of step i+1; every step's merged result is
         produced (and waited for on the timing stream) inside the timed region."""
+        if graph is not None:
+            for i in range(a, b):
+                q_static.copy_(queries[i], non_blocking=True)
+                graph.replay()
+            return g_out
         if not pipelined:
             out_ = None
             for i in range(a, b):
@@ -428,6 +450,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = frp.kernel_launches() - launches0
+    if graph is not None:
+        launches = K * launches_per_graph_step
     fallback_steps = int(out[3].item() != 0)
     if dist is not None:
         t = torch.tensor([ms], device=device)
@@ -596,6 +620,7 @@ def run_ours(args):
                 "dtype": "f16 (fp32 accumulate; fp64 re-rank of fp32 master)", "data": "synthetic",
                 "config": config(args, world), "match_path": path, "gpu_launches": int(launches),
                 "exchange": args.exchange if world > 1 else "none", "exchange_equals_nccl": exchange_check,
+                "stepping": "cuda_graph" if graph is not None else ("two_slot_pipeline" if pipelined else "plain_launches"),
                 "uncertified_last_step": fallback_steps, "clocks": clocks, "e2e": e2e, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu

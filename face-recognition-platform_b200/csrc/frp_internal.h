@@ -171,6 +171,7 @@ int match_device_locked(frp_gallery* g, const float* q_dev, size_t qstride, cons
 int pick_kp(int k);
 cudaStream_t thread_stream(int device);
 void configure_func_smem(const void* func, int device, size_t bytes, int* rc);
+void configure_func_carveout(const void* func, int device);
 
 }  // namespace frp
 

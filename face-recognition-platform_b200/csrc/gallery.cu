@@ -55,6 +55,21 @@ void configure_func_smem(const void* func, int device, size_t bytes, int* rc) {
     cur = bytes;
 }
 
+// The small kernels around the prefilter (query prep, re-rank, merge) ask for the same
+// shared-memory carve-out as the prefilter itself (all of it): when consecutive kernels on a
+// stream want different L1 / shared splits the SMs drain and reconfigure between them, which
+// showed up as tens of microseconds per step that no kernel accounted for.
+void configure_func_carveout(const void* func, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, bool> done;
+    std::lock_guard<std::mutex> lk(mu);
+    bool& d = done[std::make_pair(func, device)];
+    if (d) return;
+    cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+    d = true;
+}
+
 // One warp per row: fp64 norm, optional normalisation, fp32 master + fp16 copy.
 // src rows are `src_stride` floats apart; normalise = 0 ingests COS rows verbatim (snapshot load:
 // the stored master is already normalised and must stay bit-identical).

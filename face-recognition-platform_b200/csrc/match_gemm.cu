@@ -37,6 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "frp_device.cuh"
@@ -649,6 +650,21 @@ int pick_stages(int nkb, bool l2) {
 
 void* tensormap_encode_fn() { return reinterpret_cast<void*>(get_encode_fn()); }
 
+// SMs the prefilter leaves free (frp_set_reserved_sms): its CTAs take a whole SM's shared memory,
+// so a collective that should overlap it (the all-gather + merge of the previous step on another
+// stream) has nowhere to run unless a couple of SMs stay out of the grid
+std::atomic<int> g_reserved_sms{0};
+
+}  // namespace frp
+
+extern "C" int frp_set_reserved_sms(int n) {
+    if (n < 0 || n > 64) { frp::set_error("frp_set_reserved_sms: %d out of range [0, 64]", n); return FRP_E_INVALID; }
+    frp::g_reserved_sms.store(n);
+    return FRP_OK;
+}
+
+namespace frp {
+
 // FRP_GEMM_NO_CLUSTER=1 disables the 2-CTA multicast variant (A/B measurements)
 static const bool g_gemm_no_cluster = []() {
     const char* e = getenv("FRP_GEMM_NO_CLUSTER");
@@ -687,7 +703,9 @@ static int gemm_lpc(const frp_gallery* g) {
 
 int gemm_num_lists(const frp_gallery* g, int B) {
     const int groups = gemm_groups(B);
-    int per = g->sm_count / groups;
+    int sms = g->sm_count - g_reserved_sms.load(std::memory_order_relaxed);
+    if (sms < groups) sms = groups;
+    int per = sms / groups;
     if (per < 1) per = 1;
     const uint64_t ntiles = (g->rows + kTileN - 1) / kTileN;
     if ((uint64_t)per > ntiles) per = (int)ntiles;

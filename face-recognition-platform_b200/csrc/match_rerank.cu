@@ -571,6 +571,7 @@ push_merge_kernel(int metric, int R, int rank, int B, int k, const uint8_t* __re
 int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride, const uint64_t* q_rows,
                         int B, double tau, int flags, int eps_mode, float* qprep, __half* q16,
                         QParams* qp, cudaStream_t st) {
+    configure_func_carveout((const void*)prep_queries_kernel, g->device);
     prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, qstride, q_rows, g->dim, g->dimp, g->metric, tau, flags,
                                            eps_mode, g->gmax, g->gerr, qprep, q16, qp);
     FRP_CHECK_LAUNCH();
@@ -578,6 +579,11 @@ int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride
 }
 
 int launch_raise_cut(QParams* qp, int B, int k, const uint64_t* cand, int nlists, int KP, cudaStream_t st) {
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        configure_func_carveout((const void*)raise_cut_kernel, dev);
+    }
     raise_cut_kernel<<<B, 256, 0, st>>>(qp, k, cand, nlists * KP);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
@@ -631,6 +637,7 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
         configure_func_smem((const void*)rerank_kernel, g->device, smem, &rc);
         if (rc) return rc;
     }
+    configure_func_carveout((const void*)rerank_kernel, g->device);
     rerank_kernel<<<B, kRerankThreads, smem, st>>>(a);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
@@ -689,6 +696,11 @@ int frp_merge_packed_device(int metric, int R, int B, int k, const void* records
     const size_t o1 = (size_t)B * k * 8, o2 = o1 + (size_t)B * k * 8, o3 = o2 + (size_t)B * 4;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_any_status) FRP_CUDA(cudaMemsetAsync(out_any_status, 0, sizeof(int32_t), st));
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        configure_func_carveout((const void*)merge_topk_kernel, dev);
+    }
     merge_topk_kernel<<<B, 128, 0, st>>>(metric, R, B, k, base, base + o1, base + o2, base + o3, rec,
                                          out_idx, out_score, out_score64, out_count, out_any_status);
     FRP_CHECK_LAUNCH();

@@ -71,6 +71,7 @@ SIGNATURES = {
     "frp_shard_record_bytes": (_sz, [_i, _i]),
     "frp_match_record_device": (_i, [_vp, _vp, _i, _d, _i, _i, _vp, _vp]),
     "frp_merge_packed_device": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "frp_set_reserved_sms": (_i, [_i]),
     "frp_cluster": (_i, [_vp, _d, _i, _vp, _u64, _pi, _vp]),
     "frp_cooldown_create": (_i, [_i, _u64, C.POINTER(_vp)]),
     "frp_cooldown_destroy": (_i, [_vp]),

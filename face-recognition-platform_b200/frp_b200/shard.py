@@ -175,6 +175,29 @@ class ShardedMatcher:
         self._merge(m, self.world, B, k, recv, out_idx, out_score, out_count, any_status, stream)
         return out_idx, out_score, out_count, any_status
 
+    # -- CUDA graph of one step ---------------------------------------------------------
+    def capture(self, q_static, tau: float, k: int, flags: int = 0, metric: Optional[int] = None):
+        """Capture one step (local match -> all-gather -> merge) reading ``q_static`` into a CUDA
+        graph: a step is 5-6 short dependent launches around one long kernel, and at 8 ranks
+        (0.25 ms of kernels per step) the gaps between them are ~15 % of the step.  Returns
+        (graph, outputs): ``q_static.copy_(q); graph.replay()`` runs a step on the current
+        stream; ``outputs`` = (idx, score, count, any_fallback) device tensors it refills.
+        The warm-up step runs on the capture stream itself so every workspace the library
+        needs for that stream exists before capture starts (no allocation inside the graph)."""
+        t = self.torch
+        dev = q_static.device
+        side = t.cuda.Stream(device=dev)
+        side.wait_stream(t.cuda.current_stream(dev))
+        with t.cuda.stream(side):
+            for _ in range(2):
+                self.match(q_static, tau, k, flags, metric)
+        side.synchronize()
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g, stream=side):
+            out = self.match(q_static, tau, k, flags, metric)
+        t.cuda.current_stream(dev).wait_stream(side)
+        return g, out
+
     # -- two-slot pipeline: exchange of step i behind the prefilter of step i+1 -----------
     def _pipeline(self, device, depth: int):
         if self._pipe is None or self._pipe["device"] != device or self._pipe["depth"] != depth:
@@ -202,6 +225,13 @@ class ShardedMatcher:
         import torch.distributed as dist
         if self.exchange != "nccl":
             raise ValueError("the pipelined path uses the NCCL exchange")
+        if self.world > 1 and not getattr(self, "_reserved", False) and q_dev.device.type == "cuda":
+            # the all-gather + merge of step i must RUN while the prefilter of step i+1 holds the
+            # SMs: keep a few out of the prefilter's grid (FRP_RESERVED_SMS overrides; 0 = none)
+            import os
+            from ._capi import check, lib
+            check(lib.frp_set_reserved_sms(int(os.environ.get("FRP_RESERVED_SMS", "2"))))
+            self._reserved = True
         B = int(q_dev.shape[0])
         device = q_dev.device
         p = self._pipeline(device, depth)

@@ -174,6 +174,12 @@ int frp_push_merge_device(int metric, int R, int rank, int B, int k, const void*
                           int64_t* out_idx, float* out_score, int32_t* out_count,
                           int32_t* out_any_status, void* stream);
 
+/* Number of SMs the tcgen05 prefilter leaves out of its grid (default 0).  Its CTAs occupy a whole
+ * SM's shared memory, so work on another stream that should overlap it — the all-gather + merge
+ * of the previous step in the pipelined sharded matcher — only runs concurrently if a few SMs
+ * stay free.  Process-wide; ShardedMatcher sets 2 for its pipelined mode on more than one rank. */
+int frp_set_reserved_sms(int n);
+
 /* ---- gallery against itself: cluster_faces (face_service.py:552-585) -------------------
  * Greedy seed clustering on the device gallery: rows in insertion order; an unassigned live
  * row seeds a cluster and absorbs every unassigned live row within tau (inclusive `<=` / `>=`,
