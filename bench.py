@@ -49,9 +49,9 @@ def parse():
     ap.add_argument("--exchange", default=os.environ.get("FRP_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
                     help="multi-GPU merge: NCCL all-gather + merge kernel, or the fused peer-memory kernel")
     ap.add_argument("--also-batches", default="", help="comma list of extra batch sizes timed on the same gallery")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="two-slot pipeline (all-gather + merge of step i behind the prefilter of step i+1) instead of the CUDA graph")
-    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of one CUDA graph per step")
+    ap.add_argument("--pipeline", action="store_true", help="force the two-slot pipeline (default when more than one rank runs)")
+    ap.add_argument("--no-pipeline", action="store_true", help="plain launches on one stream at every rank count")
+    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step (opt-in)")
     ap.add_argument("--c3", choices=["auto", "on", "off"], default="auto",
                     help="100 M-row leg (12.5 M rows per rank): auto = when 8 ranks run")
     return ap.parse_args()
@@ -394,13 +394,15 @@ def run_ours(args):
     def step(i):
         return matcher.match(queries[i], tau, k)
 
-    # default stepping: one CUDA graph per step (prep -> tcgen05 prefilter -> re-rank -> all-gather
-    # -> merge are 5-6 dependent launches; their gaps are ~15 % of a 0.29 ms step at 8 ranks).
-    # --pipeline: two-slot pipeline over two streams instead; --no-graph: plain launches.
-    pipelined = args.pipeline and args.exchange == "nccl"
+    # stepping: more than one rank -> two-slot pipeline over two streams (all-gather + merge of step
+    # i behind the prefilter of step i+1: +2 % at 8 ranks, neutral at 2); one rank -> plain
+    # launches (nothing to overlap; the extra stream only adds event traffic).  --graph replays
+    # one CUDA graph per step instead (measured equal within noise at 2 ranks: sustained steps are
+    # power-capped, not launch-gap-bound).
+    pipelined = (args.pipeline or (world > 1 and not args.no_pipeline)) and args.exchange == "nccl" and not args.graph
     graph = None
     launches_per_graph_step = 0
-    if not args.no_graph and not pipelined and args.exchange == "nccl":
+    if args.graph and args.exchange == "nccl":
         try:
             q_static = queries[0].clone()
             l0 = frp.kernel_launches()
@@ -628,6 +630,9 @@ def run_ours(args):
             line["extra"] = extras
         print(json.dumps(line))
     if dist is not None:
+        graph = None            # a captured all-gather must be gone before the communicator is torn down
+        g_out = None
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
