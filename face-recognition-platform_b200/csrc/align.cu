@@ -133,6 +133,50 @@ __device__ void estimate_norm_dev(const float* lm, double* M) {
     M[3] = m10; M[4] = m00;  M[5] = dy - (m10 * sx + m00 * sy);
 }
 
+// The same estimate as insightface actually evaluates it: it hands skimage float32 landmarks and
+// the float32 template, so _umeyama's means, deviations, covariance A and variance are float32
+// (numpy keeps the dtype) while the composition (d, T, scale) is float64.  The rotation is
+// the closed form of the 2x2 SVD applied to the float32 A; LAPACK's float32 SVD rounds
+// differently in the last bits, so matrices agree with skimage-on-float32 to ~1e-6 relative,
+// not bit for bit (the float64 form above is what SURVEY 8c specifies and what frp_align uses
+// when it is given landmarks).
+__device__ void estimate_norm_f32_dev(const float* lm, double* M) {
+    const float dstf[10] = {38.2946f, 51.6963f, 73.5318f, 51.5014f, 56.0252f, 71.7366f, 41.5493f, 92.3655f, 70.7299f, 92.2041f};
+    float sx = 0.f, sy = 0.f, dx = 0.f, dy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        sx = __fadd_rn(sx, lm[2 * i]); sy = __fadd_rn(sy, lm[2 * i + 1]);
+        dx = __fadd_rn(dx, dstf[2 * i]); dy = __fadd_rn(dy, dstf[2 * i + 1]);
+    }
+    sx = __fdiv_rn(sx, 5.f); sy = __fdiv_rn(sy, 5.f); dx = __fdiv_rn(dx, 5.f); dy = __fdiv_rn(dy, 5.f);
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, px_[5], py_[5], mx = 0.f, my = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float px = __fsub_rn(lm[2 * i], sx), py = __fsub_rn(lm[2 * i + 1], sy);
+        const float qx = __fsub_rn(dstf[2 * i], dx), qy = __fsub_rn(dstf[2 * i + 1], dy);
+        a00 = __fadd_rn(a00, __fmul_rn(qx, px)); a01 = __fadd_rn(a01, __fmul_rn(qx, py));
+        a10 = __fadd_rn(a10, __fmul_rn(qy, px)); a11 = __fadd_rn(a11, __fmul_rn(qy, py));
+        px_[i] = px; py_[i] = py;
+        mx = __fadd_rn(mx, px); my = __fadd_rn(my, py);
+    }
+    a00 = __fdiv_rn(a00, 5.f); a01 = __fdiv_rn(a01, 5.f); a10 = __fdiv_rn(a10, 5.f); a11 = __fdiv_rn(a11, 5.f);
+    // numpy var: mean of squared deviations from the (float32) mean of the already demeaned data
+    mx = __fdiv_rn(mx, 5.f); my = __fdiv_rn(my, 5.f);
+    float vx = 0.f, vy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float ex = __fsub_rn(px_[i], mx), ey = __fsub_rn(py_[i], my);
+        vx = __fadd_rn(vx, __fmul_rn(ex, ex)); vy = __fadd_rn(vy, __fmul_rn(ey, ey));
+    }
+    const float var = __fadd_rn(__fdiv_rn(vx, 5.f), __fdiv_rn(vy, 5.f));
+    // float64 composition: scale * R = [[a, -b], [b, a]] * (1 / var) with a = A00 + A11, b = A10 - A01
+    const double a = (double)a00 + (double)a11, b = (double)a10 - (double)a01;
+    const double inv = 1.0 / (double)var;
+    const double m00 = a * inv, m10 = b * inv;
+    M[0] = m00; M[1] = -m10; M[2] = (double)dx - (m00 * (double)sx - m10 * (double)sy);
+    M[3] = m10; M[4] = m00;  M[5] = (double)dy - (m10 * (double)sx + m00 * (double)sy);
+}
+
 // cv::warpAffine's inversion of the forward matrix (double, operation order kept,
 // no fused multiply-add so the rounding matches the host library)
 __device__ void invert_affine_dev(const double* M, double* iM) {
@@ -602,13 +646,14 @@ align_kernel(const __grid_constant__ TmapSet maps, const __grid_constant__ Align
     }
 }
 
-__global__ void estimate_norm_kernel(const float* __restrict__ lmk, int n, double* __restrict__ M) {
+__global__ void estimate_norm_kernel(const float* __restrict__ lmk, int n, double* __restrict__ M, int f32) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float lm[10];
     for (int j = 0; j < 10; ++j) lm[j] = lmk[(size_t)i * 10 + j];
     double m[6];
-    estimate_norm_dev(lm, m);
+    if (f32) estimate_norm_f32_dev(lm, m);
+    else estimate_norm_dev(lm, m);
     for (int j = 0; j < 6; ++j) M[(size_t)i * 6 + j] = m[j];
 }
 
@@ -837,7 +882,7 @@ int frp_align(int device, const uint8_t* frames, int F, int H, int W, size_t str
     return rc;
 }
 
-int frp_estimate_norm(const float* lmk, int n, double* M_out) {
+static int estimate_norm_host(const float* lmk, int n, double* M_out, int f32) {
     if (n < 0 || !lmk || !M_out) { set_error("frp_estimate_norm: invalid argument"); return FRP_E_INVALID; }
     if (n == 0) return FRP_OK;
     int ndev = 0;
@@ -848,7 +893,7 @@ int frp_estimate_norm(const float* lmk, int n, double* M_out) {
     cudaError_t e = cudaMalloc((void**)&d_m, (size_t)n * 6 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(d_l, lmk, (size_t)n * 10 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        estimate_norm_kernel<<<(n + 127) / 128, 128>>>(d_l, n, d_m);
+        estimate_norm_kernel<<<(n + 127) / 128, 128>>>(d_l, n, d_m, f32);
         e = cudaGetLastError();
         count_launch();
     }
@@ -857,5 +902,8 @@ int frp_estimate_norm(const float* lmk, int n, double* M_out) {
     if (e != cudaSuccess) { set_error("frp_estimate_norm failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return FRP_E_CUDA; }
     return FRP_OK;
 }
+
+int frp_estimate_norm(const float* lmk, int n, double* M_out) { return estimate_norm_host(lmk, n, M_out, 0); }
+int frp_estimate_norm_f32(const float* lmk, int n, double* M_out) { return estimate_norm_host(lmk, n, M_out, 1); }
 
 }  // extern "C"

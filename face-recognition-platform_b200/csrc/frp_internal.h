@@ -127,6 +127,11 @@ int gemm_num_lists(const frp_gallery* g, int B);
 // tmap_q: the caller's cached descriptor of q16 ([groups*128][dimp] fp16), see Workspace
 int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int B, int KP,
                       uint64_t* cand, int nlists, cudaStream_t st, uint64_t rows_limit = 0);
+// galleries of a few thousand rows: everything (prep, exact scores, threshold, top-k) in one launch
+bool match_small_supported(const frp_gallery* g, int B);
+int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride, int B, double tau, int k, int flags,
+                       int64_t* out_idx, float* out_score, double* out_score64, int32_t* out_count,
+                       int32_t* out_status, cudaStream_t st);
 // pure top-k: raise every query's prefilter cut to (k-th best key of `cand`) - 2 eps
 int launch_raise_cut(QParams* qp, int B, int k, const uint64_t* cand, int nlists, int KP, cudaStream_t st);
 int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp);

@@ -123,6 +123,18 @@ int match_device_locked(frp_gallery* g, const float* q_dev, size_t qstride, cons
         set_match_path("empty");
         return FRP_OK;
     }
+    // the reference's own scale (a few thousand faces): one fused exact launch, no prefilter
+    if (!q_rows && !(flags & (FRP_MATCH_FORCE_SCAN | FRP_MATCH_FORCE_GEMM | FRP_MATCH_FORCE_EXACT | FRP_MATCH_WIDE)) &&
+        match_small_supported(g, B)) {
+        const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+        cudaEvent_t* ev = prof ? profile_events() : nullptr;
+        if (ev) { cudaEventRecord(ev[0], st); cudaEventRecord(ev[1], st); }
+        int rc = launch_match_small(g, q_dev, qstride, B, tau, k, flags, out_idx, out_score, out_score64, out_count,
+                                    out_status, st);
+        if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); t_profile_valid = true; }
+        set_match_path("small_exact");
+        return rc;
+    }
     const bool exact = (flags & FRP_MATCH_FORCE_EXACT) != 0;
     const bool wide = (flags & FRP_MATCH_WIDE) != 0;      // the ladder's last rung: 64-key lists on the scan kernel
     bool use_gemm = false;

@@ -338,6 +338,150 @@ __global__ void __launch_bounds__(256) raise_cut_kernel(QParams* __restrict__ qp
 }
 
 // ---------------------------------------------------------------------------
+// match_small: the reference's own scale (BASELINE configs[0]: 1 query vs 1 000 x 128-d) in ONE
+// launch.  A gallery of a few thousand rows needs no prefilter and no certificate: one block per
+// query normalises the query (COS), evaluates EVERY live row exactly (fp64 from the fp32 master,
+// one warp per row, the same expression and summation order as rerank_kernel, so the values are
+// bit-identical to the large-gallery path), thresholds, and extracts the top-k by k rounds of a
+// block-wide lexicographic arg-best (score, then row: stable like the reference's sort).
+// ---------------------------------------------------------------------------
+constexpr int kSmallRows = 4096;
+constexpr int kSmallThreads = 256;
+
+struct SmallArgs {
+    const float* g32;
+    const uint8_t* alive;
+    const uint64_t* seq;
+    const float* q;
+    size_t qstride;
+    int rows, dim, dimp, metric, flags, k;
+    double tau;
+    uint64_t base_row;
+    int64_t* out_idx;
+    float* out_score;
+    double* out_score64;
+    int32_t* out_count;
+    int32_t* out_status;
+};
+
+__global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallArgs a) {
+    extern __shared__ __align__(16) uint8_t small_smem[];
+    double* sc = reinterpret_cast<double*>(small_smem);                       // [rows] exact value (NaN = not a candidate)
+    float* qv = reinterpret_cast<float*>(small_smem + (size_t)a.rows * 8);    // [dimp] prepared query
+    __shared__ double red[32];
+    __shared__ double s_best_v[kSmallThreads / 32];
+    __shared__ int s_best_r[kSmallThreads / 32];
+    __shared__ double s_pick_v;
+    __shared__ int s_pick_r;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* src = a.q + (size_t)b * a.qstride;
+    // ---- query prep: same arithmetic as prep_queries_kernel ----
+    double acc = 0.0;
+    for (int i = tid; i < a.dim; i += blockDim.x) { const double x = (double)src[i]; acc += x * x; }
+    acc = warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        double t = (tid < (kSmallThreads >> 5)) ? red[tid] : 0.0;
+        t = warp_sum_f64(t);
+        if (tid == 0) red[0] = t;
+    }
+    __syncthreads();
+    const double n2 = red[0];
+    double scale = 1.0;
+    if (a.metric == FRP_METRIC_COS) scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+    for (int i = tid; i < a.dimp; i += blockDim.x) qv[i] = (i < a.dim) ? (float)((double)src[i] * scale) : 0.f;
+    __syncthreads();
+    // ---- every live row, exactly ----
+    const bool thresholded = !(a.flags & FRP_MATCH_NO_THRESHOLD);
+    const bool strict = (a.flags & FRP_MATCH_STRICT) != 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const float4* q4 = reinterpret_cast<const float4*>(qv);
+    const int nvec = a.dimp >> 2;
+    for (int row = warp; row < a.rows; row += (kSmallThreads >> 5)) {
+        const float4* gr = reinterpret_cast<const float4*>(a.g32 + (size_t)row * a.dimp);
+        double s = 0.0;
+        if (a.metric == FRP_METRIC_COS) {
+            for (int i = lane; i < nvec; i += 32) {
+                const float4 g = __ldg(gr + i);
+                const float4 q = q4[i];
+                s += (double)g.x * (double)q.x + (double)g.y * (double)q.y + (double)g.z * (double)q.z +
+                     (double)g.w * (double)q.w;
+            }
+        } else {
+            for (int i = lane; i < nvec; i += 32) {
+                const float4 g = __ldg(gr + i);
+                const float4 q = q4[i];
+                const double dx = (double)g.x - (double)q.x, dy = (double)g.y - (double)q.y;
+                const double dz = (double)g.z - (double)q.z, dw = (double)g.w - (double)q.w;
+                s += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+        }
+        s = warp_sum_f64(s);
+        if (lane == 0) {
+            double v = (a.metric == FRP_METRIC_COS) ? s : sqrt(s);
+            bool p = a.alive[row] != 0 && (v == v);
+            if (p && thresholded) {
+                if (a.metric == FRP_METRIC_COS) p = strict ? (v > a.tau) : (v >= a.tau);
+                else p = strict ? (v < a.tau) : (v <= a.tau);
+            }
+            sc[row] = p ? v : nan;
+        }
+    }
+    __syncthreads();
+    // ---- top-k: k rounds of "best candidate after the previous pick" in (value, row) order ----
+    double last_v = 0.0;
+    int last_r = -1;
+    int cnt = 0;
+    for (int r = 0; r < a.k; ++r) {
+        double bv = nan;
+        int br = -1;
+        for (int row = tid; row < a.rows; row += blockDim.x) {
+            const double v = sc[row];
+            if (!(v == v)) continue;
+            if (last_r >= 0 && !better(a.metric, last_v, (uint32_t)last_r, v, (uint32_t)row)) continue;   // already emitted
+            if (br < 0 || better(a.metric, v, (uint32_t)row, bv, (uint32_t)br)) { bv = v; br = row; }
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+            const double ov = __shfl_xor_sync(FRP_FULL_MASK, bv, sft);
+            const int orr = __shfl_xor_sync(FRP_FULL_MASK, br, sft);
+            if (orr >= 0 && (br < 0 || better(a.metric, ov, (uint32_t)orr, bv, (uint32_t)br))) { bv = ov; br = orr; }
+        }
+        if (lane == 0) { s_best_v[warp] = bv; s_best_r[warp] = br; }
+        __syncthreads();
+        if (tid == 0) {
+            double pv = nan;
+            int pr = -1;
+            for (int w = 0; w < (kSmallThreads >> 5); ++w)
+                if (s_best_r[w] >= 0 && (pr < 0 || better(a.metric, s_best_v[w], (uint32_t)s_best_r[w], pv, (uint32_t)pr))) {
+                    pv = s_best_v[w]; pr = s_best_r[w];
+                }
+            s_pick_v = pv; s_pick_r = pr;
+            if (pr >= 0) {
+                a.out_idx[(size_t)b * a.k + r] = a.seq ? (int64_t)a.seq[pr] : (int64_t)(a.base_row + (uint64_t)pr);
+                if (a.out_score) a.out_score[(size_t)b * a.k + r] = (float)pv;
+                if (a.out_score64) a.out_score64[(size_t)b * a.k + r] = pv;
+            }
+        }
+        __syncthreads();
+        if (s_pick_r < 0) break;
+        last_v = s_pick_v;
+        last_r = s_pick_r;
+        ++cnt;
+    }
+    for (int i = cnt + tid; i < a.k; i += blockDim.x) {
+        a.out_idx[(size_t)b * a.k + i] = -1;
+        if (a.out_score) a.out_score[(size_t)b * a.k + i] = __int_as_float(0x7fc00000);
+        if (a.out_score64) a.out_score64[(size_t)b * a.k + i] = nan;
+    }
+    if (tid == 0) {
+        a.out_count[b] = cnt;
+        if (a.out_status) a.out_status[b] = FRP_STATUS_OK;     // exact by construction
+    }
+}
+
+// ---------------------------------------------------------------------------
 // dense scores: one warp per gallery row, fp64 from the fp32 master.
 // ---------------------------------------------------------------------------
 __global__ void scores_kernel(const float* __restrict__ g32, const uint8_t* __restrict__ alive,
@@ -574,6 +718,23 @@ int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride
     configure_func_carveout((const void*)prep_queries_kernel, g->device);
     prep_queries_kernel<<<B, 128, 0, st>>>(q_dev, qstride, q_rows, g->dim, g->dimp, g->metric, tau, flags,
                                            eps_mode, g->gmax, g->gerr, qprep, q16, qp);
+    FRP_CHECK_LAUNCH();
+    return FRP_OK;
+}
+
+bool match_small_supported(const frp_gallery* g, int B) { return g->rows > 0 && g->rows <= (uint64_t)kSmallRows && B <= 64; }
+
+int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride, int B, double tau, int k, int flags,
+                       int64_t* out_idx, float* out_score, double* out_score64, int32_t* out_count,
+                       int32_t* out_status, cudaStream_t st) {
+    SmallArgs a;
+    a.g32 = g->g32; a.alive = g->alive; a.seq = g->seq; a.q = q_dev; a.qstride = qstride;
+    a.rows = (int)g->rows; a.dim = g->dim; a.dimp = g->dimp; a.metric = g->metric; a.flags = flags; a.k = k;
+    a.tau = tau; a.base_row = g->base_row;
+    a.out_idx = out_idx; a.out_score = out_score; a.out_score64 = out_score64; a.out_count = out_count;
+    a.out_status = out_status;
+    const size_t smem = (size_t)a.rows * 8 + (size_t)g->dimp * 4;
+    match_small_kernel<<<B, kSmallThreads, smem, st>>>(a);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }

@@ -81,6 +81,7 @@ SIGNATURES = {
     "frp_exchange_buffer_bytes": (_sz, [_i, _i, _i]),
     "frp_push_merge_device": (_i, [_i, _i, _i, _i, _i, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "frp_estimate_norm": (_i, [_vp, _i, _vp]),
+    "frp_estimate_norm_f32": (_i, [_vp, _i, _vp]),
     "frp_align": (_i, [_i, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp, _vp]),
     "frp_align_device": (_i, [_i, _vp, _i, _i, _i, _sz, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "frp_profile_enable": (_i, [_i]),

@@ -17,11 +17,20 @@ from ._capi import check, lib, ptr
 OUT = 112
 
 
-def estimate_norm(lmk) -> np.ndarray:
-    """face_align.estimate_norm for a batch: [n,5,2] fp32 -> [n,2,3] float64."""
+def estimate_norm(lmk, precision: str = "float64") -> np.ndarray:
+    """face_align.estimate_norm for a batch: [n,5,2] fp32 -> [n,2,3] float64.
+    precision="float64": skimage's Umeyama in float64 (what ``norm_crop_batch``
+    uses when given landmarks).  precision="float32": the mixed precision insightface really
+    runs (float32 landmarks + float32 template keep skimage's means / covariance / variance in
+    float32); pass the result as ``M`` to reproduce insightface's crops within 1 LSB."""
     a = np.ascontiguousarray(np.asarray(lmk, dtype=np.float32).reshape(-1, 5, 2))
     M = np.empty((a.shape[0], 6), np.float64)
-    check(lib.frp_estimate_norm(ptr(a), a.shape[0], ptr(M)))
+    if precision == "float64":
+        check(lib.frp_estimate_norm(ptr(a), a.shape[0], ptr(M)))
+    elif precision == "float32":
+        check(lib.frp_estimate_norm_f32(ptr(a), a.shape[0], ptr(M)))
+    else:
+        raise ValueError("precision must be 'float64' or 'float32'")
     return M.reshape(-1, 2, 3)
 
 

@@ -229,6 +229,12 @@ int frp_match_hits(frp_gallery_t* g, frp_cooldown_t* c, const float* queries, in
 /* 2x3 forward similarity matrices from 5 landmarks (skimage _umeyama onto
  * arcface_dst, float64).  lmk [n][5][2] fp32 host -> M [n][6] f64 host. */
 int frp_estimate_norm(const float* lmk, int n, double* M_out);
+/* The estimate as insightface 0.7.3 actually evaluates it: float32 landmarks and template make
+ * skimage's _umeyama run its means, covariance and variance in float32 (numpy keeps the dtype)
+ * and only the composition in float64.  Same closed form on those float32 intermediates;
+ * agrees with skimage-on-float32 to ~1e-6 relative (LAPACK's float32 SVD differs in the last
+ * bits).  Pass the result as `M` to frp_align to reproduce insightface's crops within 1 LSB. */
+int frp_estimate_norm_f32(const float* lmk, int n, double* M_out);
 /* frames: F BGR u8 images [F][H][stride] (stride >= 3*W bytes, host);
  * frame_idx [n]; lmk [n][5][2] fp32 (or NULL when M [n][6] f64 is given).
  * out_blob [n][3][112][112] fp16 (RGB planes, (v-127.5)/127.5);
@@ -252,7 +258,7 @@ int frp_profile_last(float* prep_ms, float* prefilter_ms, float* rerank_ms);
 int frp_profile_align_enable(int on);
 int frp_profile_align_last(float* kernel_ms);
 /* name of the kernel family the last frp_match* call of this thread used:
- * "scan_f16", "scan_f32", "gemm_tcgen05" */
+ * "small_exact" (<= 4 096 rows: one fused exact launch), "scan_f16", "scan_f32", "gemm_tcgen05" */
 const char* frp_last_match_path(void);
 
 #ifdef __cplusplus

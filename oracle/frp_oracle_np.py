@@ -347,6 +347,48 @@ def umeyama(src, dst):
     return T
 
 
+def umeyama_f32(src, dst):
+    """skimage _umeyama as insightface 0.7.3 really runs it: face_align.estimate_norm passes
+    float32 landmarks and the float32 arcface_dst, numpy keeps float32 through the means, the
+    deviations, A and the variance, LAPACK's float32 SVD (sgesdd) factors A, and only d, T and
+    the composition are float64 (skimage allocates them as float64).  TEST INFRASTRUCTURE."""
+    src = np.asarray(src, dtype=np.float32)
+    dst = np.asarray(dst, dtype=np.float32)
+    num, dim = src.shape
+    src_mean = src.mean(axis=0)
+    dst_mean = dst.mean(axis=0)
+    src_demean = src - src_mean
+    dst_demean = dst - dst_mean
+    A = dst_demean.T @ src_demean / num
+    d = np.ones((dim,), dtype=np.float64)
+    if np.linalg.det(A) < 0:
+        d[dim - 1] = -1
+    T = np.eye(dim + 1, dtype=np.float64)
+    U, S, V = np.linalg.svd(A)
+    rank = np.linalg.matrix_rank(A)
+    if rank == 0:
+        return np.nan * T
+    elif rank == dim - 1:
+        if np.linalg.det(U) * np.linalg.det(V) > 0:
+            T[:dim, :dim] = U @ V
+        else:
+            s = d[dim - 1]
+            d[dim - 1] = -1
+            T[:dim, :dim] = U @ np.diag(d) @ V
+            d[dim - 1] = s
+    else:
+        T[:dim, :dim] = U @ np.diag(d) @ V
+    scale = 1.0 / src_demean.var(axis=0).sum() * (S @ d)
+    T[:dim, dim] = dst_mean - scale * (T[:dim, :dim] @ src_mean.T)
+    T[:dim, :dim] *= scale
+    return T
+
+
+def estimate_norm_f32(lmk):
+    """insightface face_align.estimate_norm(lmk, 112) with the dtypes insightface uses."""
+    return umeyama_f32(np.asarray(lmk, dtype=np.float32).reshape(5, 2), ARCFACE_DST)[0:2, :]
+
+
 def estimate_norm(lmk):
     """face_align.estimate_norm(lmk, image_size=112): 2x3 forward affine."""
     lmk = np.asarray(lmk)

@@ -54,6 +54,31 @@ def test_1080p_crops_vs_cv2_live():
     assert worst == 0          # what the fixed-point scheme delivers
 
 
+def test_float32_estimate_reproduces_insightface_precision():
+    """insightface hands skimage float32 landmarks, so its matrices come from a float32 Umeyama
+    (oracle: umeyama_f32, LAPACK sgesdd).  frp_estimate_norm_f32 evaluates the closed form on the
+    same float32 intermediates: matrices agree to ~1e-6 relative, and crops warped with them stay
+    within north_star's 1 LSB of cv2.warpAffine on the oracle's float32 matrices."""
+    cv2 = pytest.importorskip("cv2")
+    frames = o.synth_frames(2, 1080, 1920, seed=61)
+    fi, lm = o.synth_detections(2, 64, seed=62)
+    M32 = align.estimate_norm(lm, precision="float32")
+    M64 = align.estimate_norm(lm)
+    want = np.stack([o.estimate_norm_f32(l) for l in lm])
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(M32 - want) / scale).max() < 2e-6
+    assert (np.abs(M32 - M64) / scale).max() < 2e-6 and not np.array_equal(M32, M64)
+    blob, al = align.norm_crop_batch(frames, fi, M=M32, return_aligned=True)
+    worst, differing = 0, 0
+    for i in range(len(fi)):
+        ref = cv2.warpAffine(frames[fi[i]], want[i], (112, 112), borderValue=0.0)
+        d = np.abs(ref.astype(int) - al[i].astype(int))
+        worst = max(worst, int(d.max()))
+        differing += int((d > 0).sum())
+    assert worst <= 1                                   # the gate
+    assert differing < 0.002 * al.size                  # and almost every pixel is identical
+
+
 def test_large_faces_take_the_direct_path_and_odd_strides():
     # sigma up to 8 source px per template px exceeds the per-warp staging buffer
     H, W = 700, 1001                      # 3*W = 3003 is not a multiple of 16 -> repitched on upload

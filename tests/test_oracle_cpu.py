@@ -224,3 +224,13 @@ def test_fast_topk_oracles_equal_the_plain_ones():
         b = o.l2_match_topk_fast(G2, Q2, 0.6, 10, thr, chunk=4096)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
         assert np.array_equal(a[1], b[1], equal_nan=True)
+
+
+def test_float32_umeyama_restatement():
+    """umeyama_f32 (what insightface's float32 inputs make skimage compute) stays within float32
+    round-off of the float64 estimate and is a proper similarity."""
+    fi, lm = o.synth_detections(2, 40, seed=9)
+    for l in lm:
+        a, b = o.estimate_norm(l), o.estimate_norm_f32(l)
+        assert np.abs(a - b).max() / np.abs(a).max() < 2e-6
+        assert abs(b[0, 0] - b[1, 1]) < 1e-9 * abs(b[0, 0]) + 1e-12 and abs(b[0, 1] + b[1, 0]) < 1e-9 * abs(b[0, 0]) + 1e-9

@@ -134,6 +134,62 @@ def test_large_topk_runs_on_the_tensor_cores(metric, k):
         g.close()
 
 
+@pytest.mark.parametrize("metric,dim", [(METRIC_L2, 128), (METRIC_COS, 512), (METRIC_L2, 100)])
+def test_small_galleries_take_the_fused_exact_kernel(metric, dim):
+    """BASELINE configs[0] scale (1 query vs ~1 000 faces): one fused launch, results bit-identical
+    to the prefilter + re-rank paths and equal to the oracle, including exact ties, tombstones,
+    strict thresholds, pure top-k and k = 64."""
+    from frp_b200 import MATCH_STRICT
+    rng = np.random.default_rng(dim)
+    N = 1500
+    if metric == METRIC_L2:
+        G = rng.normal(0, 0.05, (N, dim)).astype(np.float32)
+        Q = (G[rng.integers(0, N, 9)] + rng.normal(0, 0.02, (9, dim))).astype(np.float32)
+        tau = 0.6
+    else:
+        G = o.synth_cos_gallery(N, dim, seed=5)
+        Q, _ = o.synth_cos_queries(G, 9, seed=6)
+        tau = 0.3
+    G[700] = G[3]
+    G[1499] = G[3]
+    Q[0] = G[3]
+    g = Gallery(dim, metric)
+    g.append(G)
+    g.remove(11)
+    alive = np.ones(N, bool)
+    alive[11] = False
+    try:
+        for k in (1, 5, 64):
+            for flags in (0, MATCH_NO_THRESHOLD, MATCH_STRICT):
+                before = frp_b200.kernel_launches()
+                a = g.match(Q, tau, k, flags)
+                assert frp_b200.last_match_path() == "small_exact" and frp_b200.kernel_launches() == before + 1
+                assert np.all(a[3] == 0)
+                b = g.match(Q, tau, k, flags | MATCH_FORCE_SCAN)
+                assert frp_b200.last_match_path() != "small_exact"
+                for x, y in zip(a[:3], b[:3]):
+                    assert np.array_equal(x, y, equal_nan=True), (k, flags)
+                Ga = np.where(alive[:, None], G, np.nan if metric == METRIC_L2 else 0).astype(np.float32)
+                if metric == METRIC_L2:
+                    want = o.l2_match_topk(np.where(alive[:, None], G, 1e3), Q, tau, k, not (flags & MATCH_NO_THRESHOLD))
+                else:
+                    want = o.cos_match_topk(G, Q, tau, k, not (flags & MATCH_NO_THRESHOLD))
+                if flags == 0 and metric == METRIC_L2:
+                    _assert_topk_equal(a[0], a[1], a[2], *want, ("small", k))
+        assert g.match(Q[:1], tau, 5)[0][0, :3].tolist() == [3, 700, 1499]
+        # the C1 call itself: one query, 1 000-face service, all result dicts
+        enc = GalleryDict()
+        enc.bulk_load(["id%04d" % i for i in range(1000)], o.synth_l2_gallery(1000, 128, seed=1234))
+        fs = FaceService(enc, raise_errors=True)
+        q = o.synth_l2_queries(o.synth_l2_gallery(1000, 128, seed=1234), 4, seed=4321)[0]
+        ref = {n: enc[n] for n in enc.keys()}
+        for x in q:
+            assert [t for t, _ in fs.match_topk(x[None], 0.6, 5)[0]] == [r["target"] for r in o.compare_faces(ref, x, 0.6) if r["match"]][:5]
+        assert frp_b200.last_match_path() == "small_exact"
+    finally:
+        g.close()
+
+
 def test_pure_topk_sampling_pass_is_sound():
     """find_k_nearest semantics at scale: the sampling pass that lifts the prefilter cut (first
     ~1.5 % of the rows) must never lose a true neighbour — same answer as the oracle and as the
