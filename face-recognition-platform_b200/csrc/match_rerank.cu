@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256) raise_cut_kernel(QParams* __restrict__ qp
 // block-wide lexicographic arg-best (score, then row: stable like the reference's sort).
 // ---------------------------------------------------------------------------
 constexpr int kSmallRows = 4096;
-constexpr int kSmallThreads = 256;
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallUnroll = 4;      // gallery rows in flight per warp (the block is latency-bound)
 
 struct SmallArgs {
     const float* g32;
@@ -367,13 +368,14 @@ struct SmallArgs {
 __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallArgs a) {
     extern __shared__ __align__(16) uint8_t small_smem[];
     double* sc = reinterpret_cast<double*>(small_smem);                       // [rows] exact value (NaN = not a candidate)
-    float* qv = reinterpret_cast<float*>(small_smem + (size_t)a.rows * 8);    // [dimp] prepared query
+    float* qv = reinterpret_cast<float*>(small_smem + (((size_t)a.rows * 8 + 15) & ~(size_t)15));   // [dimp] prepared query
     __shared__ double red[32];
     __shared__ double s_best_v[kSmallThreads / 32];
     __shared__ int s_best_r[kSmallThreads / 32];
     __shared__ double s_pick_v;
     __shared__ int s_pick_r;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSmallThreads >> 5;
     const float* src = a.q + (size_t)b * a.qstride;
     // ---- query prep: same arithmetic as prep_queries_kernel ----
     double acc = 0.0;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
     if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (tid < 32) {
-        double t = (tid < (kSmallThreads >> 5)) ? red[tid] : 0.0;
+        double t = (tid < NW) ? red[tid] : 0.0;
         t = warp_sum_f64(t);
         if (tid == 0) red[0] = t;
     }
@@ -392,40 +394,50 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
     if (a.metric == FRP_METRIC_COS) scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
     for (int i = tid; i < a.dimp; i += blockDim.x) qv[i] = (i < a.dim) ? (float)((double)src[i] * scale) : 0.f;
     __syncthreads();
-    // ---- every live row, exactly ----
+    // ---- every live row, exactly: kSmallUnroll rows per warp in flight; each row's partial sums
+    // are accumulated in the order rerank_kernel uses, so the values are bit-identical ----
     const bool thresholded = !(a.flags & FRP_MATCH_NO_THRESHOLD);
     const bool strict = (a.flags & FRP_MATCH_STRICT) != 0;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const float4* q4 = reinterpret_cast<const float4*>(qv);
     const int nvec = a.dimp >> 2;
-    for (int row = warp; row < a.rows; row += (kSmallThreads >> 5)) {
-        const float4* gr = reinterpret_cast<const float4*>(a.g32 + (size_t)row * a.dimp);
-        double s = 0.0;
-        if (a.metric == FRP_METRIC_COS) {
-            for (int i = lane; i < nvec; i += 32) {
-                const float4 g = __ldg(gr + i);
-                const float4 q = q4[i];
-                s += (double)g.x * (double)q.x + (double)g.y * (double)q.y + (double)g.z * (double)q.z +
-                     (double)g.w * (double)q.w;
+    for (int row0 = warp * kSmallUnroll; row0 < a.rows; row0 += NW * kSmallUnroll) {
+        double s[kSmallUnroll];
+#pragma unroll
+        for (int u = 0; u < kSmallUnroll; ++u) s[u] = 0.0;
+        for (int i = lane; i < nvec; i += 32) {
+            float4 g[kSmallUnroll];
+#pragma unroll
+            for (int u = 0; u < kSmallUnroll; ++u) {
+                const int row = min(row0 + u, a.rows - 1);
+                g[u] = __ldg(reinterpret_cast<const float4*>(a.g32 + (size_t)row * a.dimp) + i);
             }
-        } else {
-            for (int i = lane; i < nvec; i += 32) {
-                const float4 g = __ldg(gr + i);
-                const float4 q = q4[i];
-                const double dx = (double)g.x - (double)q.x, dy = (double)g.y - (double)q.y;
-                const double dz = (double)g.z - (double)q.z, dw = (double)g.w - (double)q.w;
-                s += dx * dx + dy * dy + dz * dz + dw * dw;
+            const float4 q = q4[i];
+#pragma unroll
+            for (int u = 0; u < kSmallUnroll; ++u) {
+                if (a.metric == FRP_METRIC_COS) {
+                    s[u] += (double)g[u].x * (double)q.x + (double)g[u].y * (double)q.y + (double)g[u].z * (double)q.z +
+                            (double)g[u].w * (double)q.w;
+                } else {
+                    const double dx = (double)g[u].x - (double)q.x, dy = (double)g[u].y - (double)q.y;
+                    const double dz = (double)g[u].z - (double)q.z, dw = (double)g[u].w - (double)q.w;
+                    s[u] += dx * dx + dy * dy + dz * dz + dw * dw;
+                }
             }
         }
-        s = warp_sum_f64(s);
-        if (lane == 0) {
-            double v = (a.metric == FRP_METRIC_COS) ? s : sqrt(s);
-            bool p = a.alive[row] != 0 && (v == v);
-            if (p && thresholded) {
-                if (a.metric == FRP_METRIC_COS) p = strict ? (v > a.tau) : (v >= a.tau);
-                else p = strict ? (v < a.tau) : (v <= a.tau);
+#pragma unroll
+        for (int u = 0; u < kSmallUnroll; ++u) {
+            const double t = warp_sum_f64(s[u]);
+            const int row = row0 + u;
+            if (lane == 0 && row < a.rows) {
+                double v = (a.metric == FRP_METRIC_COS) ? t : sqrt(t);
+                bool p = a.alive[row] != 0 && (v == v);
+                if (p && thresholded) {
+                    if (a.metric == FRP_METRIC_COS) p = strict ? (v > a.tau) : (v >= a.tau);
+                    else p = strict ? (v < a.tau) : (v <= a.tau);
+                }
+                sc[row] = p ? v : nan;
             }
-            sc[row] = p ? v : nan;
         }
     }
     __syncthreads();
@@ -450,18 +462,22 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
         }
         if (lane == 0) { s_best_v[warp] = bv; s_best_r[warp] = br; }
         __syncthreads();
-        if (tid == 0) {
-            double pv = nan;
-            int pr = -1;
-            for (int w = 0; w < (kSmallThreads >> 5); ++w)
-                if (s_best_r[w] >= 0 && (pr < 0 || better(a.metric, s_best_v[w], (uint32_t)s_best_r[w], pv, (uint32_t)pr))) {
-                    pv = s_best_v[w]; pr = s_best_r[w];
+        if (warp == 0) {
+            double pv = s_best_v[lane];
+            int pr = s_best_r[lane];
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+                const double ov = __shfl_xor_sync(FRP_FULL_MASK, pv, sft);
+                const int orr = __shfl_xor_sync(FRP_FULL_MASK, pr, sft);
+                if (orr >= 0 && (pr < 0 || better(a.metric, ov, (uint32_t)orr, pv, (uint32_t)pr))) { pv = ov; pr = orr; }
+            }
+            if (lane == 0) {
+                s_pick_v = pv; s_pick_r = pr;
+                if (pr >= 0) {
+                    a.out_idx[(size_t)b * a.k + r] = a.seq ? (int64_t)a.seq[pr] : (int64_t)(a.base_row + (uint64_t)pr);
+                    if (a.out_score) a.out_score[(size_t)b * a.k + r] = (float)pv;
+                    if (a.out_score64) a.out_score64[(size_t)b * a.k + r] = pv;
                 }
-            s_pick_v = pv; s_pick_r = pr;
-            if (pr >= 0) {
-                a.out_idx[(size_t)b * a.k + r] = a.seq ? (int64_t)a.seq[pr] : (int64_t)(a.base_row + (uint64_t)pr);
-                if (a.out_score) a.out_score[(size_t)b * a.k + r] = (float)pv;
-                if (a.out_score64) a.out_score64[(size_t)b * a.k + r] = pv;
             }
         }
         __syncthreads();
@@ -733,7 +749,7 @@ int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride,
     a.tau = tau; a.base_row = g->base_row;
     a.out_idx = out_idx; a.out_score = out_score; a.out_score64 = out_score64; a.out_count = out_count;
     a.out_status = out_status;
-    const size_t smem = (size_t)a.rows * 8 + (size_t)g->dimp * 4;
+    const size_t smem = (((size_t)a.rows * 8 + 15) & ~(size_t)15) + (size_t)g->dimp * 4;
     match_small_kernel<<<B, kSmallThreads, smem, st>>>(a);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
