@@ -271,7 +271,7 @@ int frp_match_hits(frp_gallery_t* g, frp_cooldown_t* c, const float* queries, in
     const size_t o_n = o_st + al((size_t)B * 4), o_hits = o_n + 256;
     const size_t total = o_hits + al((size_t)B * k * sizeof(frp_hit_t));
     // scratch bound as in frp_match (covers every prefilter configuration)
-    const size_t cand = (size_t)(g->sm_count + 8) * 2 * 64;
+    const size_t cand = (size_t)g->sm_count * 64 + 64;
     const size_t scratch = al(al((size_t)B * g->dimp * 4) + al((size_t)(((B + 127) / 128) * 128) * g->dimp * 2) +
                               al((size_t)B * sizeof(QParams)) + al((size_t)B * cand * 8) + 1024);
     Workspace* w = workspace_for(g->device, st);

@@ -326,9 +326,9 @@ int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, 
     const HostLayout L(B, g->dim, k);
     Workspace* w = workspace_for(g->device, st);
     // device block: [match scratch (sized for the widest configuration) | queries | results];
-    // pinned block: queries | results.  The scratch bound covers every prefilter (at most
-    // 2 lists per SM x 64 keys, or 1 list per SM x 64), so the nested reserve never regrows.
-    const size_t scratch = align256(match_scratch_bytes(g, B, (size_t)(g->sm_count + 8) * 2 * 64));
+    // pinned block: queries | results.  The scratch bound covers every prefilter (tcgen05: at most
+    // 2 lists per SM x 32 keys; scan: 1 list per SM x 64 keys), so the nested reserve never regrows.
+    const size_t scratch = align256(match_scratch_bytes(g, B, (size_t)g->sm_count * 64 + 64));
     rc = workspace_reserve(w, scratch + L.total, L.total);
     if (rc) return rc;
     uint8_t* d = w->dev + scratch;
@@ -346,9 +346,14 @@ int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, 
     // caller's buffer is pinned); large pinned batches are copied from where they are
     const void* qsrc = queries;
     if (qb <= 65536 || !is_pinned_host(queries)) { memcpy(h + L.off_q, queries, qb); qsrc = h + L.off_q; }
+    const uint8_t* block0 = w->dev;
     cudaError_t e = cudaMemcpyAsync(dq, qsrc, qb, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
         rc = match_device_locked(g, dq, (size_t)g->dim, nullptr, B, tau, k, flags, pick_kp(k), di, ds, nullptr, dc, dt, st);
+    if (rc == FRP_OK && w->dev != block0) {      // cannot happen while the scratch bound above holds
+        set_error("frp_match: workspace moved under the staging area");
+        return FRP_E_NOMEM;
+    }
     // ONE device->host copy of idx | score | count | status
     if (e == cudaSuccess && rc == FRP_OK)
         e = cudaMemcpyAsync(h + L.off_i, d + L.off_i, L.result_bytes(), cudaMemcpyDeviceToHost, st);
