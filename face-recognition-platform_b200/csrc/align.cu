@@ -271,7 +271,11 @@ __global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __gri
             const double sy = iM[3] * (cx * (kOut - 1)) + iM[4] * (cy * (kOut - 1)) + iM[5];
             far = far || !(fabs(sx) < 29000.0 && fabs(sy) < 29000.0);
         }
+#ifdef FRP_ALIGN_FORCE_TH8
+    const bool th16 = fit16 && !fit8;          // experiment: 8-row tiles wherever they fit
+#else
     const bool th16 = fit16;
+#endif
     const bool direct = !(a.use_tma && !far && (fit16 || fit8));
     const int wi = th16 ? wi16 : wi8, hi = th16 ? hi16 : hi8;
     const int th1 = th16 ? 15 : 7;
@@ -290,7 +294,11 @@ __global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __gri
         // 8-row tiles (large faces only) stay single-buffered: their double-buffered form faulted on
         // B200 ("illegal memory access" from the staged kernel, every address audited in range)
         // and is not worth the risk for the ~20 % of crops that use it
+#ifdef FRP_ALIGN_DUAL8
+        const bool dual = !direct && h.box_bytes <= kHalfBuf;      // experiment: 8-row tiles double-buffered too
+#else
         const bool dual = !direct && th16 && h.box_bytes <= kHalfBuf;
+#endif
 #endif
         h.flags = (direct ? 1 : 0) | (dual ? 2 : 0) | (th16 ? 0 : 4);
         h.pad[0] = h.pad[1] = h.pad[2] = 0;
@@ -318,6 +326,11 @@ __global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar_saddr, uint32_t dst_saddr, int c0,
                                             int c1, int c2) {
+#ifdef FRP_ALIGN_ABL_NOTMA
+    // ablation (timing only, wrong pixels): no staging; tile_expect completes the phase by itself
+    (void)map; (void)bar_saddr; (void)dst_saddr; (void)c0; (void)c1; (void)c2;
+    return;
+#endif
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst_saddr), "l"(map), "r"(bar_saddr), "r"(c0), "r"(c1), "r"(c2)
@@ -330,6 +343,15 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst_saddr, const void* src, 
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar_saddr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_saddr), "r"(bytes) : "memory");
+}
+// arm a tile barrier for one TMA box
+__device__ __forceinline__ void tile_expect(uint32_t bar_saddr, uint32_t bytes) {
+#ifdef FRP_ALIGN_ABL_NOTMA
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+    (void)bytes;
+#else
+    mbar_expect_tx_a(bar_saddr, bytes);
+#endif
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar_saddr, uint32_t parity) {
     asm volatile(
@@ -397,23 +419,43 @@ __device__ __forceinline__ void blend_px(unsigned p0lo, unsigned p0hi, unsigned 
 // c/32768 and the exactly representable constant -(1 + 256 c) yields round(v c - 1):
 // fp16(fma(v, c, -1)) == fp16((v - 127.5) * c) for all 256 values (checked exhaustively in
 // tests/test_oracle_cpu.py::test_norm_fma_form_matches_cv2)
-__device__ __forceinline__ unsigned short norm_half(unsigned acc) {
+__device__ __forceinline__ unsigned short norm_half(unsigned acc, unsigned mask, unsigned magic) {
     constexpr float c = (float)(1.0 / 127.5);
-    const float f = __uint_as_float(0x4B000000u | (acc & 0x7F8000u));
-    const float n = __fmaf_rn(f, c * (1.0f / 32768.0f), -(1.0f + 256.0f * c));
+    // (acc & 0x7F8000) | 0x4B000000 as ONE three-input LOP3: mask and magic arrive in registers
+    // (two immediates would split it into two ALU-pipe instructions, and the ALU pipe — LOP3 /
+    // SHF / PRMT at half rate — is the busiest unit of this kernel)
+    unsigned bits;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bits) : "r"(acc), "r"(mask), "r"(magic));
+    const float n = __fmaf_rn(__uint_as_float(bits), c * (1.0f / 32768.0f), -(1.0f + 256.0f * c));
     return __half_as_ushort(__float2half_rn(n));
+}
+// opaque register constants for norm_half (the compiler must not fold them back into immediates)
+__device__ __forceinline__ void norm_consts(unsigned& mask, unsigned& magic) {
+    asm volatile("mov.u32 %0, 0x7F8000;" : "=r"(mask));
+    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
 }
 
 // BGR -> RGB planes; a half-warp writes 16 consecutive halfs (one 32-byte sector) per plane row
 template <int NJ>
 __device__ __forceinline__ void store_px(unsigned short* o16, uint8_t* o8, const unsigned (&vB)[NJ],
                                          const unsigned (&vG)[NJ], const unsigned (&vR)[NJ]) {
+    unsigned mask, magic;
+    norm_consts(mask, magic);
+#ifdef FRP_ALIGN_ABL_NOSTORE
+    // ablation (timing only): the values are computed, the plane stores are skipped unless a
+    // sum takes a value it cannot have (keeps the blend alive)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+        if ((vR[j] | vG[j] | vB[j]) == 0xffffffffu)
+            o16[j] = norm_half(vR[j], mask, magic) + norm_half(vG[j], mask, magic) + norm_half(vB[j], mask, magic);
+#else
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        o16[(size_t)j * 2 * kOut] = norm_half(vR[j]);
-        o16[(size_t)kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vG[j]);
-        o16[(size_t)2 * kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vB[j]);
+        o16[(size_t)j * 2 * kOut] = norm_half(vR[j], mask, magic);
+        o16[(size_t)kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vG[j], mask, magic);
+        o16[(size_t)2 * kOut * kOut + (size_t)j * 2 * kOut] = norm_half(vB[j], mask, magic);
     }
+#endif
     if (o8) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -459,8 +501,13 @@ __device__ __forceinline__ void blend_tile_staged(uint32_t tabs, uint32_t buf_sa
 #endif
         const unsigned shf = off << 3;                    // funnel shifts use the low 5 bits
         const unsigned fx = (X >> 5) & 31, ty = Y & 0x3E0;
+#ifdef FRP_ALIGN_ABL_NOTAPS
+        // ablation (timing only, wrong pixels): no tap loads, operands from registers
+        const unsigned a0 = w0, a1 = w1, a2 = (unsigned)X, b0 = (unsigned)Y, b1 = shf, b2 = w0 ^ w1;
+#else
         const unsigned a0 = lds32(w0), a1 = lds32(w0 + 4), a2 = lds32_if3(w0 + 8, off, (unsigned)X);
         const unsigned b0 = lds32(w1), b1 = lds32(w1 + 4), b2 = lds32_if3(w1 + 8, off, (unsigned)Y);
+#endif
         blend_px(__funnelshift_r(a0, a1, shf), __funnelshift_r(a1, a2, shf), __funnelshift_r(b0, b1, shf),
                  __funnelshift_r(b1, b2, shf), fx, ty, vB[j], vG[j], vR[j]);
     }
@@ -540,7 +587,7 @@ __device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps
         for (int t = 0; t < NT; ++t) {
             const int2 org = lds64(orgs + 8 * t);
             if (lane == 0) {
-                mbar_expect_tx_a(bar_tile, (uint32_t)h.box_bytes);
+                tile_expect(bar_tile, (uint32_t)h.box_bytes);
                 tma_load_3d(map, bar_tile, buf_saddr0, org.x, org.y, h.frame);
             }
             mbar_wait_a(bar_tile, parity & 1u);
@@ -554,7 +601,7 @@ __device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps
     // two half buffers: the next tile's box is in flight while this one is blended
     int2 cur = lds64(orgs);
     if (lane == 0) {
-        mbar_expect_tx_a(bar_tile, (uint32_t)h.box_bytes);
+        tile_expect(bar_tile, (uint32_t)h.box_bytes);
         tma_load_3d(map, bar_tile, buf_saddr0, cur.x, cur.y, h.frame);
     }
 #pragma unroll 1
@@ -564,7 +611,7 @@ __device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps
         if (t + 1 < NT) {
             nxt = lds64(orgs + 8 * (t + 1));
             if (lane == 0) {
-                mbar_expect_tx_a(bar_tile + 8 * (b ^ 1), (uint32_t)h.box_bytes);
+                tile_expect(bar_tile + 8 * (b ^ 1), (uint32_t)h.box_bytes);
                 tma_load_3d(map, bar_tile + 8 * (b ^ 1), buf_saddr0 + (uint32_t)((b ^ 1) * kHalfBuf), nxt.x, nxt.y,
                             h.frame);
             }
