@@ -342,6 +342,29 @@ int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, 
     const size_t ib = (size_t)B * k * sizeof(int64_t), sb = (size_t)B * k * sizeof(float);
     const size_t cb = (size_t)B * sizeof(int32_t);
 
+    // The reference's own scale (<= 4 096 faces): the fused exact kernel reads the queries from and
+    // writes the results to the pinned staging block directly (mapped host memory under UVA): one
+    // launch and one stream sync, no copy operations at all.
+    if (!(flags & (FRP_MATCH_FORCE_SCAN | FRP_MATCH_FORCE_GEMM | FRP_MATCH_FORCE_EXACT | FRP_MATCH_WIDE)) &&
+        match_small_supported(g, B)) {
+        memcpy(h + L.off_q, queries, qb);
+        rc = launch_match_small(g, reinterpret_cast<const float*>(h + L.off_q), (size_t)g->dim, B, tau, k, flags,
+                                reinterpret_cast<int64_t*>(h + L.off_i), reinterpret_cast<float*>(h + L.off_s), nullptr,
+                                reinterpret_cast<int32_t*>(h + L.off_c), reinterpret_cast<int32_t*>(h + L.off_t), st);
+        set_match_path("small_exact");
+        cudaError_t es = cudaStreamSynchronize(st);
+        if (es != cudaSuccess) {
+            set_error("frp_match: CUDA error: %s", cudaGetErrorString(es));
+            cudaGetLastError();
+            return FRP_E_CUDA;
+        }
+        if (rc) return rc;
+        memcpy(out_idx, h + L.off_i, ib);
+        memcpy(out_score, h + L.off_s, sb);
+        memcpy(out_count, h + L.off_c, cb);
+        if (out_status) memcpy(out_status, h + L.off_t, cb);
+        return FRP_OK;
+    }
     // small batches are staged (a 2 KB memcpy is cheaper than asking the driver whether the
     // caller's buffer is pinned); large pinned batches are copied from where they are
     const void* qsrc = queries;
