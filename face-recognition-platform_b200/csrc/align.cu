@@ -291,14 +291,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32) align_plan_kernel(const __gri
 #ifdef FRP_ALIGN_NODUAL
         const bool dual = false;                   // A/B switch: single buffering only
 #else
-        // 8-row tiles (large faces only) stay single-buffered: their double-buffered form faulted on
-        // B200 ("illegal memory access" from the staged kernel, every address audited in range)
-        // and is not worth the risk for the ~20 % of crops that use it
-#ifdef FRP_ALIGN_DUAL8
-        const bool dual = !direct && h.box_bytes <= kHalfBuf;      // experiment: 8-row tiles double-buffered too
-#else
-        const bool dual = !direct && th16 && h.box_bytes <= kHalfBuf;
-#endif
+        const bool dual = !direct && h.box_bytes <= kHalfBuf;
 #endif
         h.flags = (direct ? 1 : 0) | (dual ? 2 : 0) | (th16 ? 0 : 4);
         h.pad[0] = h.pad[1] = h.pad[2] = 0;
@@ -607,9 +600,18 @@ __device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
         const int b = t & 1;
+        // The table base is re-materialised through an opaque move every iteration.  Without it the
+        // 8-row instantiation of this loop faulted ("illegal memory access") on every crop: its SASS
+        // advances one register by 8 bytes per tile as the origin pointer (tabs + 8 t) AND uses
+        // it as the base of the first row pair's (X0, Y0) load, while rows 1.. use a loop-invariant
+        // copy — coordinates of row 0 came from the wrong table entries from tile 1 on
+        // (tools/align_bisect.py found it; 16-row tiles compiled correctly and stayed bit-exact).
+        uint32_t tabs_i = tabs;
+        asm volatile("" : "+r"(tabs_i));
+        const uint32_t orgs_i = tabs_i + kCommonBytes + 128;
         int2 nxt = cur;
         if (t + 1 < NT) {
-            nxt = lds64(orgs + 8 * (t + 1));
+            nxt = lds64(orgs_i + 8 * (t + 1));
             if (lane == 0) {
                 tile_expect(bar_tile + 8 * (b ^ 1), (uint32_t)h.box_bytes);
                 tma_load_3d(map, bar_tile + 8 * (b ^ 1), buf_saddr0 + (uint32_t)((b ^ 1) * kHalfBuf), nxt.x, nxt.y,
@@ -618,7 +620,7 @@ __device__ __forceinline__ void run_band(const AlignArgs& a, const TmapSet& maps
         }
         mbar_wait_a(bar_tile + 8 * b, (parity >> b) & 1u);
         parity ^= (1u << b);
-        blend_tile_staged<TH>(tabs, buf_saddr0 + (uint32_t)(b * kHalfBuf), cur.x, cur.y, pitch,
+        blend_tile_staged<TH>(tabs_i, buf_saddr0 + (uint32_t)(b * kHalfBuf), cur.x, cur.y, pitch,
                               (t % kTilesX) * kTileW, (t / kTilesX) * TH, lane, o16, o8);
         __syncwarp();      // every lane is done with buffer b before it is refilled
         cur = nxt;
