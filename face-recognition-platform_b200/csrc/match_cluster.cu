@@ -86,24 +86,28 @@ extern "C" int frp_cluster(frp_gallery_t* g, double tau, int flags, int32_t* lab
     const size_t off_cnt = off_idx + (size_t)kSlab * kNbr * sizeof(int64_t);
     const size_t off_st = off_cnt + kSlab * sizeof(int32_t);
     const size_t slab_bytes = off_st + kSlab * sizeof(int32_t);
+    // slab staging lives in the calling thread's workspace (device block behind the match scratch,
+    // pinned block): no allocation per call
     uint8_t* d_slab = nullptr; uint8_t* h_slab = nullptr;
     uint32_t* d_dense = nullptr; unsigned int* d_dense_cnt = nullptr;
     std::vector<uint32_t> h_dense;
-    cudaError_t e = cudaMalloc((void**)&d_slab, slab_bytes);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&h_slab, slab_bytes);
     int rc = FRP_OK;
+    {
+        auto al = [](size_t n) { return (n + 255) & ~(size_t)255; };
+        const size_t cand = (size_t)g->sm_count * 64 + 64;
+        const size_t scratch = al(al((size_t)kSlab * g->dimp * 4) + al((size_t)(((kSlab + 127) / 128) * 128) * g->dimp * 2) +
+                                  al((size_t)kSlab * sizeof(QParams)) + al((size_t)kSlab * cand * 8) + 1024);
+        Workspace* w = workspace_for(g->device, st);
+        rc = workspace_reserve(w, scratch + al(slab_bytes), al(slab_bytes));
+        if (rc) return rc;
+        d_slab = w->dev + scratch;
+        h_slab = w->pinned;
+    }
+    cudaError_t e = cudaSuccess;
     auto cleanup = [&]() {
-        if (d_slab) cudaFree(d_slab);
-        if (h_slab) cudaFreeHost(h_slab);
         if (d_dense) cudaFree(d_dense);
         if (d_dense_cnt) cudaFree(d_dense_cnt);
     };
-    if (e != cudaSuccess) {
-        set_error("frp_cluster: staging allocation failed: %s", cudaGetErrorString(e));
-        cleanup();
-        cudaGetLastError();
-        return FRP_E_NOMEM;
-    }
     uint64_t* h_rows = reinterpret_cast<uint64_t*>(h_slab + off_rows);
     const int64_t* h_idx = reinterpret_cast<const int64_t*>(h_slab + off_idx);
     const int32_t* h_cnt = reinterpret_cast<const int32_t*>(h_slab + off_cnt);
