@@ -129,9 +129,12 @@ int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int
                       uint64_t* cand, int nlists, cudaStream_t st, uint64_t rows_limit = 0);
 // galleries of a few thousand rows: everything (prep, exact scores, threshold, top-k) in one launch
 bool match_small_supported(const frp_gallery* g, int B);
+// q_host (optional): host-readable copy of the same queries; small blocks ride in the kernel parameters
 int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride, int B, double tau, int k, int flags,
                        int64_t* out_idx, float* out_score, double* out_score64, int32_t* out_count,
-                       int32_t* out_status, cudaStream_t st);
+                       int32_t* out_status, cudaStream_t st, unsigned int* done_count = nullptr,
+                       volatile unsigned int* done_flag = nullptr, unsigned int done_seq = 0,
+                       const float* q_host = nullptr);
 // pure top-k: raise every query's prefilter cut to (k-th best key of `cand`) - 2 eps
 int launch_raise_cut(QParams* qp, int B, int k, const uint64_t* cand, int nlists, int KP, cudaStream_t st);
 int encode_query_map(void* tmap_out, const __half* q16, int groups, int dimp);
@@ -165,6 +168,10 @@ struct Workspace {
     alignas(64) unsigned char tmap_q[128];
     const void* q16_ptr = nullptr;
     int q_groups = 0, q_dimp = 0;
+    // completion word of the small-gallery kernel: device counter + mapped host flag + sequence
+    unsigned int* done_count = nullptr;
+    volatile unsigned int* done_flag = nullptr;
+    unsigned int done_seq = 0;
 };
 Workspace* workspace_for(int device, cudaStream_t st);
 int workspace_reserve(Workspace* w, size_t dev_bytes, size_t pinned_bytes);

@@ -8,7 +8,10 @@
 // the gallery's TMA descriptors are cached in the gallery (gallery.cu / match_gemm.cu), the
 // query descriptor in the workspace, and the host API moves its results with ONE D2H copy
 // through pinned staging.
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include <map>
 #include <mutex>
@@ -348,11 +351,51 @@ int frp_match(frp_gallery_t* g, const float* queries, int B, double tau, int k, 
     if (!(flags & (FRP_MATCH_FORCE_SCAN | FRP_MATCH_FORCE_GEMM | FRP_MATCH_FORCE_EXACT | FRP_MATCH_WIDE)) &&
         match_small_supported(g, B)) {
         memcpy(h + L.off_q, queries, qb);
+        // completion: the kernel publishes a sequence number in mapped host memory and the host
+        // polls that word (a stream synchronisation costs several microseconds more than the
+        // kernel itself at this size); the stream is queried now and then so that a failed kernel
+        // still ends the wait.  FRP_SMALL_POLL=0 falls back to cudaStreamSynchronize.
+        static const bool poll_enabled = []() { const char* e = getenv("FRP_SMALL_POLL"); return !(e && e[0] == '0'); }();
+        if (poll_enabled && !w->done_flag) {
+            unsigned int* hf = nullptr;
+            unsigned int* dc0 = nullptr;
+            if (cudaMallocHost((void**)&hf, 64) == cudaSuccess && cudaMalloc((void**)&dc0, 4) == cudaSuccess &&
+                cudaMemset(dc0, 0, 4) == cudaSuccess) {
+                *hf = 0;
+                w->done_flag = hf; w->done_count = dc0;
+            } else {
+                cudaGetLastError();
+                if (hf) cudaFreeHost(hf);
+                if (dc0) cudaFree(dc0);
+            }
+        }
+        const bool poll = poll_enabled && w->done_flag;
+        const unsigned int seq = poll ? ++w->done_seq : 0;
         rc = launch_match_small(g, reinterpret_cast<const float*>(h + L.off_q), (size_t)g->dim, B, tau, k, flags,
                                 reinterpret_cast<int64_t*>(h + L.off_i), reinterpret_cast<float*>(h + L.off_s), nullptr,
-                                reinterpret_cast<int32_t*>(h + L.off_c), reinterpret_cast<int32_t*>(h + L.off_t), st);
+                                reinterpret_cast<int32_t*>(h + L.off_c), reinterpret_cast<int32_t*>(h + L.off_t), st,
+                                poll ? w->done_count : nullptr, poll ? w->done_flag : nullptr, seq, queries);
         set_match_path("small_exact");
-        cudaError_t es = cudaStreamSynchronize(st);
+        cudaError_t es = cudaSuccess;
+        if (poll && rc == FRP_OK) {
+            unsigned int spins = 0;
+            while (*w->done_flag != seq) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                if ((++spins & 0xfff) == 0) {
+                    const cudaError_t qe = cudaStreamQuery(st);
+                    if (qe == cudaErrorNotReady) continue;
+                    es = qe;                      // finished (the flag is set by now) or failed
+                    if (qe != cudaSuccess || *w->done_flag == seq) break;
+                    es = cudaStreamSynchronize(st);
+                    break;
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        } else {
+            es = cudaStreamSynchronize(st);
+        }
         if (es != cudaSuccess) {
             set_error("frp_match: CUDA error: %s", cudaGetErrorString(es));
             cudaGetLastError();

@@ -97,19 +97,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -129,11 +116,75 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return r;
 }
 
+
+// The MMA issuer runs warp-convergent: every lane executes the statement and ONE lane, chosen by
+// elect.sync inside it, issues the instruction.  Under a divergent `if (lane == 0)` ptxas wraps
+// each tcgen05 instruction (uniform-datapath operands) in an ELECT / PLOP3 / BRA.U.ANY loop over
+// the active lanes; with 128-d rows (two K blocks per tile) that made the issuer warp, not the
+// tensor pipe, the critical path.  FRP_MMA_ELECT=0 rebuilds the old form (measurement aid).
+#ifndef FRP_MMA_ELECT
+#define FRP_MMA_ELECT 1
+#endif
+#if FRP_MMA_ELECT
+#define FRP_ELECT_DECL ".reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+#define FRP_ELECT_PRED "@e "
+#else
+#define FRP_ELECT_DECL ""
+#define FRP_ELECT_PRED ""
+#endif
+template <int CTA_GROUP>
+__device__ __forceinline__ void umma_f16_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    if (CTA_GROUP == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t" FRP_ELECT_DECL
+            "setp.ne.b32 p, %4, 0;\n\t"
+            FRP_ELECT_PRED "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t" FRP_ELECT_DECL
+            "setp.ne.b32 p, %4, 0;\n\t"
+            FRP_ELECT_PRED "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// commit to this CTA's barrier (cta_group::1, no multicast)
+__device__ __forceinline__ void umma_commit_issue(uint64_t* bar) {
+    asm volatile(
+        "{\n\t" FRP_ELECT_DECL FRP_ELECT_PRED
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+// commit multicast to the barrier at the same offset in every CTA of `mask`
+template <int CTA_GROUP>
+__device__ __forceinline__ void umma_commit_mc_issue(uint64_t* bar, uint16_t mask) {
+    if (CTA_GROUP == 1) {
+        asm volatile(
+            "{\n\t" FRP_ELECT_DECL FRP_ELECT_PRED
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(smem_u32(bar)), "h"(mask)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t" FRP_ELECT_DECL FRP_ELECT_PRED
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(smem_u32(bar)), "h"(mask)
+            : "memory");
+    }
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
-// start address >> 4 | LBO = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
+// start address >> 4 | LBO = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2,
+// built in two halves: the low word carries the start address (>> 4) and LBO, so stepping
+// to the next K slice or ring slot is one integer add (shared memory ends below 2^18, the
+// 14-bit address field cannot carry); the high word is constant.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t lo) {
+    constexpr uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
 }
 
 // kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M=128, N=256
@@ -168,12 +219,6 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
         "[%0], [%1, {%4, %5}], [%2], %3;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
 
@@ -390,7 +435,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         tc_fence_after();
         int s = 0;
         uint32_t ph = 0;
-        const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem_a)), b_lo0 = smem_desc_lo(smem_u32(smem_b));
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t as = i & 1;
             mbar_wait(&tempty_bar[as], ((i >> 1) & 1) ^ 1);     // epilogue drained this TMEM stage
@@ -399,19 +444,20 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             for (int kb = 0; kb < a.nkb; ++kb) {
                 mbar_wait(&full_bar[s], ph);                    // TMA landed this gallery K block
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = a_base + (uint32_t)kb * kABlockBytes;
-                    const uint32_t b_addr = b_base + (uint32_t)s * kBStageBytes;
+#if !FRP_MMA_ELECT
+                if (lane == 0)
+#endif
+                {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)kb * (kABlockBytes >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBStageBytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK * 2);
-                        const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
-                        umma_f16(tmem_d, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_f16_issue<1>(tmem_d, smem_desc(a_lo + k * (kUmmaK * 2 >> 4)),
+                                          smem_desc(b_lo + k * (kUmmaK * 2 >> 4)), kIdesc, (kb | k) != 0 ? 1u : 0u);
                     // frees the smem slot (in every CTA of the cluster) when the MMAs retire
-                    if (CS > 1) umma_commit_mc(&empty_bar[s], (uint16_t)0x3);
-                    else umma_commit(&empty_bar[s]);
-                    if (kb == a.nkb - 1) umma_commit(&tfull_bar[as]);   // accumulator ready
+                    if (CS > 1) umma_commit_mc_issue<1>(&empty_bar[s], (uint16_t)0x3);
+                    else umma_commit_issue(&empty_bar[s]);
+                    if (kb == a.nkb - 1) umma_commit_issue(&tfull_bar[as]);   // accumulator ready
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -450,21 +496,6 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(mask)
-        : "memory");
 }
 // dst in this CTA's shared memory, completion bytes on the barrier at cluster address bar_caddr
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_caddr, void* dst, int c0, int c1) {
@@ -564,7 +595,7 @@ match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             tc_fence_after();
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem_a)), b_lo0 = smem_desc_lo(smem_u32(smem_b));
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t as = i & 1;
                 mbar_wait(&tempty_bar[as], ((i >> 1) & 1) ^ 1);     // both CTAs drained this TMEM stage
@@ -573,17 +604,19 @@ match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     mbar_wait(&full_bar[s], ph);                    // both halves of the K block landed
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_addr = a_base + (uint32_t)kb * kABlockBytes;
-                        const uint32_t b_addr = b_base + (uint32_t)s * kBHalfBytes;
+#if !FRP_MMA_ELECT
+                    if (lane == 0)
+#endif
+                    {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)kb * (kABlockBytes >> 4);
+                        const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBHalfBytes >> 4);
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK * 2);
-                            const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
-                            umma_f16_2(tmem_d, adesc, bdesc, kIdescPair, (kb | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit2_mc(&empty_bar[s], (uint16_t)0x3);              // slot free in both CTAs
-                        if (kb == a.nkb - 1) umma_commit2_mc(&tfull_bar[as], (uint16_t)0x3);   // accumulators ready
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            umma_f16_issue<2>(tmem_d, smem_desc(a_lo + k * (kUmmaK * 2 >> 4)),
+                                              smem_desc(b_lo + k * (kUmmaK * 2 >> 4)), kIdescPair,
+                                              (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_mc_issue<2>(&empty_bar[s], (uint16_t)0x3);              // slot free in both CTAs
+                        if (kb == a.nkb - 1) umma_commit_mc_issue<2>(&tfull_bar[as], (uint16_t)0x3);   // accumulators ready
                     }
                     __syncwarp();
                     if (++s == a.stages) { s = 0; ph ^= 1; }

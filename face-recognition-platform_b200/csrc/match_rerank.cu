@@ -342,12 +342,21 @@ __global__ void __launch_bounds__(256) raise_cut_kernel(QParams* __restrict__ qp
 // launch.  A gallery of a few thousand rows needs no prefilter and no certificate: one block per
 // query normalises the query (COS), evaluates EVERY live row exactly (fp64 from the fp32 master,
 // one warp per row, the same expression and summation order as rerank_kernel, so the values are
-// bit-identical to the large-gallery path), thresholds, and extracts the top-k by k rounds of a
-// block-wide lexicographic arg-best (score, then row: stable like the reference's sort).
+// bit-identical to the large-gallery path) and thresholds.  Top-k in (score, then row) order, stable
+// like the reference's sort: up to 32 candidates (the usual thresholded query) are ranked by one
+// warp; more (pure top-k) go through per-warp k-best lists and a ranking of their union.
 // ---------------------------------------------------------------------------
+// The rows of one query are split over a cluster of kSmallCluster CTAs (8 SMs pull the gallery
+// instead of one); every CTA stores its exact values into CTA 0's shared memory (DSMEM), and CTA 0
+// extracts the top-k after one cluster barrier.  `done_flag` (mapped host memory, optional): the
+// last block to finish publishes `done_seq` there after a system fence, so the host can poll one
+// word instead of paying a stream synchronisation.
 constexpr int kSmallRows = 4096;
-constexpr int kSmallThreads = 1024;
+constexpr int kSmallCluster = 8;
+constexpr int kSmallInline = 512;    // floats of query data carried in the kernel parameters
+constexpr int kSmallRank = 32;       // up to this many candidates are ranked by one warp
 constexpr int kSmallUnroll = 4;      // gallery rows in flight per warp (the block is latency-bound)
+constexpr int small_threads(int cs) { return cs == 1 ? 1024 : 512; }
 
 struct SmallArgs {
     const float* g32;
@@ -363,37 +372,74 @@ struct SmallArgs {
     double* out_score64;
     int32_t* out_count;
     int32_t* out_status;
+    unsigned int* done_count;        // device counter of finished queries (zero between launches)
+    volatile unsigned int* done_flag;   // mapped host word, or null
+    unsigned int done_seq;
+    // a query block of up to kSmallInline floats travels in the kernel parameters themselves (the
+    // single-query compare_faces call): no trip over PCIe before the first gallery row is read
+    int inline_q;
+    float qinline[kSmallInline];
 };
 
-__global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallArgs a) {
+__device__ __forceinline__ uint32_t small_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void small_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void small_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void small_store_rank0(double* local_ptr, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(0));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+template <int CS>
+__global__ void __launch_bounds__(small_threads(CS)) match_small_kernel(const __grid_constant__ SmallArgs a) {
+    constexpr int kSmallThreads = small_threads(CS);
     extern __shared__ __align__(16) uint8_t small_smem[];
     double* sc = reinterpret_cast<double*>(small_smem);                       // [rows] exact value (NaN = not a candidate)
     float* qv = reinterpret_cast<float*>(small_smem + (((size_t)a.rows * 8 + 15) & ~(size_t)15));   // [dimp] prepared query
     __shared__ double red[32];
-    __shared__ double s_best_v[kSmallThreads / 32];
-    __shared__ int s_best_r[kSmallThreads / 32];
-    __shared__ double s_pick_v;
-    __shared__ int s_pick_r;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_ncand, s_nunion;
+    __shared__ int s_cand[kSmallRank];
+    __shared__ int s_union[(small_threads(CS) / 32) * 64];     // every warp's k <= 64 best rows
+    const int b = (CS == 1) ? blockIdx.x : blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kSmallThreads >> 5;
+    const int rank = (CS == 1) ? 0 : (int)small_cluster_rank();
+    if (CS > 1) small_cluster_arrive();      // CTA 0's shared memory exists once every CTA has arrived
+    // this CTA's slice of the rows (whole groups of kSmallUnroll)
+    const int per = (((a.rows + CS - 1) / CS + kSmallUnroll - 1) / kSmallUnroll) * kSmallUnroll;
+    const int lo = min(rank * per, a.rows), hi = min(lo + per, a.rows);
     const float* src = a.q + (size_t)b * a.qstride;
-    // ---- query prep: same arithmetic as prep_queries_kernel ----
-    double acc = 0.0;
-    for (int i = tid; i < a.dim; i += blockDim.x) { const double x = (double)src[i]; acc += x * x; }
-    acc = warp_sum_f64(acc);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (tid < 32) {
-        double t = (tid < NW) ? red[tid] : 0.0;
-        t = warp_sum_f64(t);
-        if (tid == 0) red[0] = t;
+    // ---- query prep.  The raw query is staged once (it may live in mapped host memory: one trip
+    // over PCIe); |q|^2 is summed in prep_queries_kernel's order (128 strided partial sums, warp
+    // butterflies, then 4 -> 1), so the prepared query is bit-identical to the large-gallery path ----
+    if (tid == 0) { s_ncand = 0; s_nunion = 0; }
+    if (a.inline_q) {
+        for (int i = tid; i < a.dimp; i += blockDim.x) qv[i] = (i < a.dim) ? a.qinline[b * a.dim + i] : 0.f;
+    } else {
+        for (int i = tid; i < a.dimp; i += blockDim.x) qv[i] = (i < a.dim) ? src[i] : 0.f;
     }
     __syncthreads();
-    const double n2 = red[0];
-    double scale = 1.0;
-    if (a.metric == FRP_METRIC_COS) scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
-    for (int i = tid; i < a.dimp; i += blockDim.x) qv[i] = (i < a.dim) ? (float)((double)src[i] * scale) : 0.f;
-    __syncthreads();
+    if (a.metric == FRP_METRIC_COS) {
+        double acc = 0.0;
+        if (tid < 128)
+            for (int i = tid; i < a.dim; i += 128) { const double x = (double)qv[i]; acc += x * x; }
+        acc = warp_sum_f64(acc);
+        if (lane == 0 && warp < 4) red[warp] = acc;
+        __syncthreads();
+        if (tid < 32) {
+            double t = (tid < 4) ? red[tid] : 0.0;
+            t = warp_sum_f64(t);
+            if (tid == 0) red[0] = t;
+        }
+        __syncthreads();
+        const double n2 = red[0];
+        const double scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+        for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = (float)((double)qv[i] * scale);
+        __syncthreads();
+    }
     // ---- every live row, exactly: kSmallUnroll rows per warp in flight; each row's partial sums
     // are accumulated in the order rerank_kernel uses, so the values are bit-identical ----
     const bool thresholded = !(a.flags & FRP_MATCH_NO_THRESHOLD);
@@ -401,7 +447,8 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const float4* q4 = reinterpret_cast<const float4*>(qv);
     const int nvec = a.dimp >> 2;
-    for (int row0 = warp * kSmallUnroll; row0 < a.rows; row0 += NW * kSmallUnroll) {
+    if (CS > 1) small_cluster_wait();
+    for (int row0 = lo + warp * kSmallUnroll; row0 < hi; row0 += NW * kSmallUnroll) {
         double s[kSmallUnroll];
 #pragma unroll
         for (int u = 0; u < kSmallUnroll; ++u) s[u] = 0.0;
@@ -429,62 +476,107 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
         for (int u = 0; u < kSmallUnroll; ++u) {
             const double t = warp_sum_f64(s[u]);
             const int row = row0 + u;
-            if (lane == 0 && row < a.rows) {
+            if (lane == 0 && row < hi) {
                 double v = (a.metric == FRP_METRIC_COS) ? t : sqrt(t);
                 bool p = a.alive[row] != 0 && (v == v);
                 if (p && thresholded) {
                     if (a.metric == FRP_METRIC_COS) p = strict ? (v > a.tau) : (v >= a.tau);
                     else p = strict ? (v < a.tau) : (v <= a.tau);
                 }
-                sc[row] = p ? v : nan;
+                if (CS == 1) sc[row] = p ? v : nan;
+                else small_store_rank0(&sc[row], p ? v : nan);
             }
         }
     }
-    __syncthreads();
-    // ---- top-k: k rounds of "best candidate after the previous pick" in (value, row) order ----
+    if (CS > 1) {
+        small_cluster_arrive();
+        small_cluster_wait();
+        if (rank != 0) return;
+    } else {
+        __syncthreads();
+    }
+    // ---- top-k.  The usual thresholded query has a handful of candidates: list them, and when
+    // there are at most kSmallRank one warp ranks them (rank = number of candidates that are
+    // better in (value, row) order: a strict total order, so the ranks are a permutation) ----
     double last_v = 0.0;
     int last_r = -1;
     int cnt = 0;
-    for (int r = 0; r < a.k; ++r) {
-        double bv = nan;
-        int br = -1;
-        for (int row = tid; row < a.rows; row += blockDim.x) {
-            const double v = sc[row];
-            if (!(v == v)) continue;
-            if (last_r >= 0 && !better(a.metric, last_v, (uint32_t)last_r, v, (uint32_t)row)) continue;   // already emitted
-            if (br < 0 || better(a.metric, v, (uint32_t)row, bv, (uint32_t)br)) { bv = v; br = row; }
+    for (int row0 = 0; row0 < a.rows; row0 += blockDim.x) {      // one shared atomic per warp, not per row
+        const int row = row0 + tid;
+        const bool is_cand = row < a.rows && sc[row] == sc[row];
+        const unsigned int m = __ballot_sync(FRP_FULL_MASK, is_cand);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_ncand, __popc(m));
+            base = __shfl_sync(FRP_FULL_MASK, base, 0);
+            const int p = base + __popc(m & ((1u << lane) - 1u));
+            if (is_cand && p < kSmallRank) s_cand[p] = row;
         }
-#pragma unroll
-        for (int sft = 16; sft >= 1; sft >>= 1) {
-            const double ov = __shfl_xor_sync(FRP_FULL_MASK, bv, sft);
-            const int orr = __shfl_xor_sync(FRP_FULL_MASK, br, sft);
-            if (orr >= 0 && (br < 0 || better(a.metric, ov, (uint32_t)orr, bv, (uint32_t)br))) { bv = ov; br = orr; }
-        }
-        if (lane == 0) { s_best_v[warp] = bv; s_best_r[warp] = br; }
-        __syncthreads();
+    }
+    __syncthreads();
+    const int ncand = s_ncand;
+    if (ncand <= kSmallRank) {
         if (warp == 0) {
-            double pv = s_best_v[lane];
-            int pr = s_best_r[lane];
+            const int mr = (lane < ncand) ? s_cand[lane] : -1;
+            const double mv = (mr >= 0) ? sc[mr] : nan;
+            int rk = 0;
+            for (int j = 0; j < ncand; ++j) {
+                const double ov = __shfl_sync(FRP_FULL_MASK, mv, j);
+                const int orr = __shfl_sync(FRP_FULL_MASK, mr, j);
+                if (mr >= 0 && better(a.metric, ov, (uint32_t)orr, mv, (uint32_t)mr)) ++rk;
+            }
+            if (mr >= 0 && rk < a.k) {
+                a.out_idx[(size_t)b * a.k + rk] = a.seq ? (int64_t)a.seq[mr] : (int64_t)(a.base_row + (uint64_t)mr);
+                if (a.out_score) a.out_score[(size_t)b * a.k + rk] = (float)mv;
+                if (a.out_score64) a.out_score64[(size_t)b * a.k + rk] = mv;
+            }
+        }
+        cnt = min(ncand, a.k);
+    }
+    // More candidates than one warp ranks (pure top-k, wide thresholds).  Stage 1: every warp
+    // takes a contiguous slice of the rows and extracts ITS k best by k rounds of a warp-wide
+    // arg-best (shuffles only, no block barrier).  Stage 2: the union (at most NW * k rows, it
+    // contains the global top-k) is ranked by counting, all threads.
+    if (ncand > kSmallRank) {
+        const int slice = (a.rows + NW - 1) / NW;
+        const int w_lo = min(warp * slice, a.rows), w_hi = min(w_lo + slice, a.rows);
+        for (int r = 0; r < a.k; ++r) {
+            double bv = nan;
+            int br = -1;
+            for (int row = w_lo + lane; row < w_hi; row += 32) {
+                const double v = sc[row];
+                if (!(v == v)) continue;
+                if (last_r >= 0 && !better(a.metric, last_v, (uint32_t)last_r, v, (uint32_t)row)) continue;   // already listed
+                if (br < 0 || better(a.metric, v, (uint32_t)row, bv, (uint32_t)br)) { bv = v; br = row; }
+            }
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) {
-                const double ov = __shfl_xor_sync(FRP_FULL_MASK, pv, sft);
-                const int orr = __shfl_xor_sync(FRP_FULL_MASK, pr, sft);
-                if (orr >= 0 && (pr < 0 || better(a.metric, ov, (uint32_t)orr, pv, (uint32_t)pr))) { pv = ov; pr = orr; }
+                const double ov = __shfl_xor_sync(FRP_FULL_MASK, bv, sft);
+                const int orr = __shfl_xor_sync(FRP_FULL_MASK, br, sft);
+                if (orr >= 0 && (br < 0 || better(a.metric, ov, (uint32_t)orr, bv, (uint32_t)br))) { bv = ov; br = orr; }
             }
-            if (lane == 0) {
-                s_pick_v = pv; s_pick_r = pr;
-                if (pr >= 0) {
-                    a.out_idx[(size_t)b * a.k + r] = a.seq ? (int64_t)a.seq[pr] : (int64_t)(a.base_row + (uint64_t)pr);
-                    if (a.out_score) a.out_score[(size_t)b * a.k + r] = (float)pv;
-                    if (a.out_score64) a.out_score64[(size_t)b * a.k + r] = pv;
-                }
-            }
+            if (br < 0) break;                       // warp-uniform after the butterfly
+            if (lane == 0) s_union[atomicAdd(&s_nunion, 1)] = br;
+            last_v = bv;
+            last_r = br;
         }
         __syncthreads();
-        if (s_pick_r < 0) break;
-        last_v = s_pick_v;
-        last_r = s_pick_r;
-        ++cnt;
+        const int nu = s_nunion;
+        for (int e = tid; e < nu; e += blockDim.x) {
+            const int mr = s_union[e];
+            const double mv = sc[mr];
+            int rk = 0;
+            for (int j2 = 0; j2 < nu; ++j2) {
+                const int orr = s_union[j2];
+                if (better(a.metric, sc[orr], (uint32_t)orr, mv, (uint32_t)mr)) ++rk;
+            }
+            if (rk < a.k) {
+                a.out_idx[(size_t)b * a.k + rk] = a.seq ? (int64_t)a.seq[mr] : (int64_t)(a.base_row + (uint64_t)mr);
+                if (a.out_score) a.out_score[(size_t)b * a.k + rk] = (float)mv;
+                if (a.out_score64) a.out_score64[(size_t)b * a.k + rk] = mv;
+            }
+        }
+        cnt = min(ncand, a.k);
     }
     for (int i = cnt + tid; i < a.k; i += blockDim.x) {
         a.out_idx[(size_t)b * a.k + i] = -1;
@@ -494,6 +586,20 @@ __global__ void __launch_bounds__(kSmallThreads) match_small_kernel(const SmallA
     if (tid == 0) {
         a.out_count[b] = cnt;
         if (a.out_status) a.out_status[b] = FRP_STATUS_OK;     // exact by construction
+    }
+    if (a.done_flag) {
+        // every result word of this query was written by this block: barrier, then a system-scope
+        // fence (cumulative over the barrier), then count; the last query publishes the sequence
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned int nq = (CS == 1) ? gridDim.x : gridDim.y;
+            if (atomicAdd(a.done_count, 1u) + 1u == nq) {
+                *a.done_count = 0;
+                __threadfence_system();
+                *a.done_flag = a.done_seq;
+            }
+        }
     }
 }
 
@@ -740,17 +846,50 @@ int launch_prep_queries(const frp_gallery* g, const float* q_dev, size_t qstride
 
 bool match_small_supported(const frp_gallery* g, int B) { return g->rows > 0 && g->rows <= (uint64_t)kSmallRows && B <= 64; }
 
+// FRP_SMALL_CLUSTER=0: one CTA per query instead of a cluster of kSmallCluster (measurement aid)
+static const bool g_small_cluster = []() {
+    const char* e = getenv("FRP_SMALL_CLUSTER");
+    return !(e && e[0] == '0');
+}();
+
 int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride, int B, double tau, int k, int flags,
                        int64_t* out_idx, float* out_score, double* out_score64, int32_t* out_count,
-                       int32_t* out_status, cudaStream_t st) {
+                       int32_t* out_status, cudaStream_t st, unsigned int* done_count,
+                       volatile unsigned int* done_flag, unsigned int done_seq, const float* q_host) {
     SmallArgs a;
     a.g32 = g->g32; a.alive = g->alive; a.seq = g->seq; a.q = q_dev; a.qstride = qstride;
     a.rows = (int)g->rows; a.dim = g->dim; a.dimp = g->dimp; a.metric = g->metric; a.flags = flags; a.k = k;
     a.tau = tau; a.base_row = g->base_row;
     a.out_idx = out_idx; a.out_score = out_score; a.out_score64 = out_score64; a.out_count = out_count;
     a.out_status = out_status;
+    a.done_count = done_count; a.done_flag = done_count ? done_flag : nullptr; a.done_seq = done_seq;
+    a.inline_q = 0;
+    if (q_host && (size_t)B * g->dim <= (size_t)kSmallInline && qstride == (size_t)g->dim) {
+        memcpy(a.qinline, q_host, (size_t)B * g->dim * sizeof(float));
+        a.inline_q = 1;
+    }
     const size_t smem = (((size_t)a.rows * 8 + 15) & ~(size_t)15) + (size_t)g->dimp * 4;
-    match_small_kernel<<<B, kSmallThreads, smem, st>>>(a);
+    // a handful of rows per CTA is not worth the cluster barrier
+    if (g_small_cluster && a.rows >= 64) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kSmallCluster, (unsigned)B, 1);
+        cfg.blockDim = dim3(small_threads(kSmallCluster), 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kSmallCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, match_small_kernel<kSmallCluster>, a);
+        if (e != cudaSuccess) {
+            set_error("match_small launch failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return FRP_E_CUDA;
+        }
+        count_launch();
+        return FRP_OK;
+    }
+    match_small_kernel<1><<<B, small_threads(1), smem, st>>>(a);
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }

@@ -190,6 +190,42 @@ def test_small_galleries_take_the_fused_exact_kernel(metric, dim):
         g.close()
 
 
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 257, 1001, 4096])
+def test_small_gallery_rows_split_over_the_cluster(rows):
+    """The fused small-gallery kernel splits a query's rows over a cluster of CTAs: ragged row
+    counts (not a multiple of cluster size x rows in flight), tombstones in every slice, batches
+    of 1 and 64, and repeated calls (the completion word counts up) must all give the answer of
+    the prefilter + re-rank route, bit for bit, and of the oracle."""
+    rng = np.random.default_rng(rows)
+    G = rng.normal(0, 0.05, (rows, 128)).astype(np.float32)
+    Q = (G[rng.integers(0, rows, 64)] + rng.normal(0, 0.02, (64, 128))).astype(np.float32)
+    g = Gallery(128, METRIC_L2)
+    g.append(G)
+    dead = sorted(set(rng.integers(0, rows, max(rows // 9, 0)).tolist())) if rows > 8 else []
+    for r in dead:
+        g.remove(r)
+    Gd = G.copy()
+    Gd[dead] = 1e3
+    try:
+        for B in (1, 64):
+            for k in (3, 64):        # pure top-k: per-warp lists + union ranking when > 32 rows
+                a = g.match(Q[:B], 0.6, k, MATCH_NO_THRESHOLD)
+                assert frp_b200.last_match_path() == "small_exact"
+                b = g.match(Q[:B], 0.6, k, MATCH_NO_THRESHOLD | MATCH_FORCE_SCAN)
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y, equal_nan=True), (rows, B, k)
+            for rep in range(3):
+                a = g.match(Q[:B], 0.6, 10)
+                assert frp_b200.last_match_path() == "small_exact"
+                b = g.match(Q[:B], 0.6, 10, MATCH_FORCE_SCAN)
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y, equal_nan=True), (rows, B, rep)
+            want = o.l2_match_topk(Gd, Q[:B], 0.6, 10, True)
+            _assert_topk_equal(a[0], a[1], a[2], *want, ("cluster split", rows, B))
+    finally:
+        g.close()
+
+
 def test_pure_topk_sampling_pass_is_sound():
     """find_k_nearest semantics at scale: the sampling pass that lifts the prefilter cut (first
     ~1.5 % of the rows) must never lose a true neighbour — same answer as the oracle and as the
