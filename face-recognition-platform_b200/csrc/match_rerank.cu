@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(small_threads(CS)) match_small_kernel(const __
     // More candidates than one warp ranks (pure top-k, wide thresholds).  Stage 1: every warp
     // takes a contiguous slice of the rows and extracts ITS k best by k rounds of a warp-wide
     // arg-best (shuffles only, no block barrier).  Stage 2: the union (at most NW * k rows, it
-    // contains the global top-k) is ranked by counting, all threads.
+    // contains the global top-k) is ranked by counting, one thread per listed row (one warp per
+    // listed row with the lanes striding the union measured no faster).
     if (ncand > kSmallRank) {
         const int slice = (a.rows + NW - 1) / NW;
         const int w_lo = min(warp * slice, a.rows), w_hi = min(w_lo + slice, a.rows);
