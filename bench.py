@@ -988,6 +988,10 @@ def side_measurements(args, frp, torch, gal, queries, pk, device, keep):
                             "tflops": fl_ / tm_ / 1e12, "tensor_frac_of_burst": fl_ / tm_ / 1e12 / pk["tensor_burst"],
                             "tensor_frac_of_sustained": fl_ / tm_ / 1e12 / pk["tensor"],
                             "mean_matches_per_query": float(bo[2].float().mean().item())}
+            # which roofline binds: B flop per gallery byte against the ridge of the measured peaks
+            ridge_ = pk["tensor"] * 1e12 / (pk["hbm"] * 1e9)
+            res[str(Bx)]["bound"] = "tensor" if Bx > ridge_ else "hbm"
+            res[str(Bx)]["ridge_flop_per_byte"] = ridge_
         out["match_l2_128d"] = {"workload": "L2, tolerance 0.6, 4M x 128 gallery (256 B fp16 rows), half the queries "
                                             "planted on rows spread over the whole gallery", "batches": res}
         g2.close()
