@@ -56,6 +56,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// ---- programmatic dependent launch ------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the
+// previous kernel of the stream is still running; it must not touch that kernel's results before
+// griddep_wait() (returns at once when the launch was an ordinary one).  griddep_launch() in the
+// earlier kernel lets the next one be scheduled as soon as every CTA has issued it.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

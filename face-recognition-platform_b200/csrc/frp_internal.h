@@ -184,6 +184,8 @@ int pick_kp(int k);
 cudaStream_t thread_stream(int device);
 void configure_func_smem(const void* func, int device, size_t bytes, int* rc);
 void configure_func_carveout(const void* func, int device);
+// programmatic dependent launches between the kernels of one match (FRP_PDL=0 turns them off)
+bool pdl_enabled();
 
 }  // namespace frp
 

@@ -40,6 +40,11 @@ cudaStream_t thread_stream(int device) {
     return st[device];
 }
 
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("FRP_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 Workspace* workspace_for(int device, cudaStream_t st) {
     static thread_local std::map<std::pair<int, cudaStream_t>, Workspace> t_ws;
     Workspace& w = t_ws[std::make_pair(device, st)];

@@ -241,6 +241,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmArgs& a, const int warp
     const int q = qgroup * kTileM + quad * 32 + lane;
     const bool valid_q = q < a.B;
     const float ninf = __int_as_float(0xff800000);
+    griddep_wait();        // the cut comes from prep_queries_kernel (or raise_cut_kernel)
     float cut0 = valid_q ? a.qp[q].cut0 : __int_as_float(0x7f800000);
     float cut = cut0;
     float ls[KP];
@@ -390,14 +391,24 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+    griddep_launch();      // the re-rank launch is staged behind this kernel (it waits for its end)
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            mbar_expect_tx(afull_bar, (uint32_t)a.nkb * kABlockBytes);
-            for (int kb = 0; kb < a.nkb; ++kb)
-                tma_load_2d(&tmap_q, afull_bar, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK, qgroup * kTileM);
-        }
+        // The gallery ring is filled first: this kernel may have started while prep_queries_kernel
+        // is still running (programmatic dependent launch), and the gallery does not depend on it.
+        // The queries are fetched after the first `stages` K blocks, behind griddep_wait().
+        auto load_queries = [&]() {
+            if (lane == 0) {
+                griddep_wait();
+                mbar_expect_tx(afull_bar, (uint32_t)a.nkb * kABlockBytes);
+                for (int kb = 0; kb < a.nkb; ++kb)
+                    tma_load_2d(&tmap_q, afull_bar, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK, qgroup * kTileM);
+            }
+            __syncwarp();
+        };
+        bool q_pending = true;
+        int issued = 0;
         int s = 0;
         uint32_t ph = 0;
         for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -427,8 +438,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1; }
+                if (q_pending && ++issued == a.stages) { load_queries(); q_pending = false; }
             }
         }
+        if (q_pending) load_queries();
     } else if (warp == 1) {
         // ================= MMA issuer =================
         mbar_wait(afull_bar, 0);
@@ -551,6 +564,7 @@ match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    griddep_launch();      // the re-rank launch is staged behind this kernel (it waits for its end)
     // cluster addresses of the leader's barriers
     const uint32_t full_leader = mapa_u32(smem_u32(full_bar), 0);
     const uint32_t afull_leader = mapa_u32(smem_u32(afull_bar), 0);
@@ -558,12 +572,19 @@ match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
-            if (crank == 0) mbar_expect_tx(afull_bar, 2u * (uint32_t)a.nkb * kABlockBytes);
-            for (int kb = 0; kb < a.nkb; ++kb)
-                tma_load_2d_2sm(&tmap_q, afull_leader, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK,
-                                qgroup * kTileM);
-        }
+        // gallery ring first, queries behind griddep_wait() (see match_gemm_kernel)
+        auto load_queries = [&]() {
+            if (lane == 0) {
+                griddep_wait();
+                if (crank == 0) mbar_expect_tx(afull_bar, 2u * (uint32_t)a.nkb * kABlockBytes);
+                for (int kb = 0; kb < a.nkb; ++kb)
+                    tma_load_2d_2sm(&tmap_q, afull_leader, smem_a + (size_t)kb * kABlockBytes, kb * kBlockK,
+                                    qgroup * kTileM);
+            }
+            __syncwarp();
+        };
+        bool q_pending = true;
+        int issued = 0;
         int s = 0;
         uint32_t ph = 0;
         for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -586,8 +607,10 @@ match_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1; }
+                if (q_pending && ++issued == a.stages) { load_queries(); q_pending = false; }
             }
         }
+        if (q_pending) load_queries();
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
         if (crank == 0) {
@@ -800,13 +823,16 @@ int launch_match_gemm(frp_gallery* g, const void* tmap_q, const QParams* qp, int
     cfg.blockDim = dim3(threads_for(lpc));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = (unsigned)cs;
     attr[0].val.clusterDim.z = 1;
+    // programmatic dependent of the kernel before it in the stream (prep_queries / raise_cut)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t le = cudaSuccess;
     if (cs == 2 && use_pair_kernel(g)) {
         // CTA-pair kernel: cluster (2,1,1) = the two query groups of one 256-query slab

@@ -34,6 +34,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, size_t qstride,
                                     QParams* __restrict__ qp) {
     __shared__ double red[32];
     __shared__ double red2[32];
+    griddep_launch();      // the prefilter may set itself up (barriers, TMEM, first gallery tiles) meanwhile
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float* src = q + (q_rows ? (size_t)q_rows[b] : (size_t)b) * qstride;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const RerankArgs
     __shared__ uint32_t ex_row[kRCap];
     __shared__ uint8_t ex_pass[kRCap];
 
+    griddep_wait();        // launched as a programmatic dependent of the prefilter
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -955,7 +957,24 @@ int launch_rerank(const frp_gallery* g, const float* qprep, const QParams* qp, i
         if (rc) return rc;
     }
     configure_func_carveout((const void*)rerank_kernel, g->device);
-    rerank_kernel<<<B, kRerankThreads, smem, st>>>(a);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)B);
+        cfg.blockDim = dim3(kRerankThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, rerank_kernel, a);
+        if (le != cudaSuccess) {
+            set_error("rerank launch failed: %s", cudaGetErrorString(le));
+            cudaGetLastError();
+            return FRP_E_CUDA;
+        }
+    }
     FRP_CHECK_LAUNCH();
     return FRP_OK;
 }
