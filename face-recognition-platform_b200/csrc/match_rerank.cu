@@ -883,14 +883,14 @@ int launch_match_small(const frp_gallery* g, const float* q_dev, size_t qstride,
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kSmallCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, match_small_kernel<kSmallCluster>, a);
-        if (e != cudaSuccess) {
-            set_error("match_small launch failed: %s", cudaGetErrorString(e));
-            cudaGetLastError();
-            return FRP_E_CUDA;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, match_small_kernel<kSmallCluster>, a);
+        if (e == cudaSuccess) {
+            count_launch();
+            return FRP_OK;
         }
-        count_launch();
-        return FRP_OK;
+        // a device partition that cannot co-schedule 8 CTAs refuses the cluster launch (not a
+        // sticky error): the one-CTA form of the same kernel below computes the same values
+        cudaGetLastError();
     }
     match_small_kernel<1><<<B, small_threads(1), smem, st>>>(a);
     FRP_CHECK_LAUNCH();
