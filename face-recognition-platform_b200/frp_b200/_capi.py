@@ -113,16 +113,28 @@ def check(rc: int) -> None:
         raise FrpError(rc, last_error())
 
 
+_c_char = C.c_char
+
+
 def ptr(a) -> int:
-    """Raw address of a C-contiguous numpy array, a torch tensor, an int, or None."""
+    """Raw address of a C-contiguous numpy array, a torch tensor, an int, or None.
+
+    numpy: ``ndarray.ctypes.data`` builds a helper object per access (~1.7 us); the buffer-protocol
+    route is three times cheaper, which matters for a 30 us call that passes five pointers.  It
+    needs a writable, non-empty buffer; anything else takes the slow route."""
     if a is None:
         return None
-    if isinstance(a, int):
+    if type(a) is int:
         return a
     if isinstance(a, np.ndarray):
-        if not a.flags["C_CONTIGUOUS"]:
+        if not a.flags.c_contiguous:
             raise ValueError("array must be C-contiguous")
-        return a.ctypes.data
+        try:
+            return C.addressof(_c_char.from_buffer(a))
+        except (TypeError, ValueError):
+            return a.ctypes.data
+    if isinstance(a, int):
+        return int(a)
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
     raise TypeError("cannot take the address of %r" % type(a))

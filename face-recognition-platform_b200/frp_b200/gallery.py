@@ -209,16 +209,26 @@ class Gallery:
 
     def match(self, queries, tau: float, k: int, flags: int = 0):
         """Host-buffer 1:N match.  Returns (idx[B,k] int64, score[B,k] f32, count[B], status[B])."""
-        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
+        q = queries
+        if not (type(q) is np.ndarray and q.dtype == np.float32 and q.ndim == 2 and q.flags.c_contiguous):
+            q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float32)))
         if q.shape[1] != self.dim:
             raise ValueError("expected queries of length %d, got %d" % (self.dim, q.shape[1]))
         B = q.shape[0]
-        idx = np.empty((B, k), np.int64)
-        score = np.empty((B, k), np.float32)
-        count = np.empty(B, np.int32)
-        status = np.empty(B, np.int32)
-        check(lib.frp_match(self.handle, ptr(q), B, float(tau), int(k), int(flags), ptr(idx), ptr(score),
-                            ptr(count), ptr(status)))
+        k = int(k)
+        # the four results are views of ONE buffer (idx | score | count | status): one address
+        # look-up instead of four (the single-query call is ~30 us, a look-up costs 0.6-1.7 us)
+        o_s = B * k * 8
+        o_c = o_s + B * k * 4
+        o_t = o_c + B * 4
+        buf = np.empty(o_t + B * 4 + 8, np.uint8)
+        idx = np.ndarray((B, k), np.int64, buf, 0)
+        score = np.ndarray((B, k), np.float32, buf, o_s)
+        count = np.ndarray((B,), np.int32, buf, o_c)
+        status = np.ndarray((B,), np.int32, buf, o_t)
+        base = ptr(buf)
+        check(lib.frp_match(self.handle, ptr(q), B, float(tau), k, int(flags), base, base + o_s, base + o_c,
+                            base + o_t))
         return idx, score, count, status
 
     def match_device(self, q_dev, B: int, tau: float, k: int, flags: int, out_idx, out_score, out_count,

@@ -205,3 +205,26 @@ def test_built_library_contains_the_blackwell_instructions():
     for op in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG.2D", "UTMALDG.2D.2CTA", "UTMALDG.2D.MULTICAST",
                "UTMALDG.3D", "UBLKCP", "UTCBAR.2CTA.MULTICAST", "IDP.2A"):
         assert op in sass, op
+
+
+def test_ptr_returns_the_array_address_on_every_route():
+    """_capi.ptr: the buffer-protocol fast route and the ndarray.ctypes fallback (read-only and
+    empty arrays) give the same address; views carry their offset; strided arrays are refused."""
+    import ctypes as C
+    from frp_b200._capi import ptr
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    assert ptr(a) == a.ctypes.data
+    assert C.cast(ptr(a), C.POINTER(C.c_float))[5] == 5.0
+    ro = np.frombuffer(b"\x00" * 16, np.float32)
+    assert not ro.flags.writeable and ptr(ro) == ro.ctypes.data
+    empty = np.empty((0, 4), np.float32)
+    assert ptr(empty) == empty.ctypes.data
+    buf = np.empty(96, np.uint8)
+    idx = np.ndarray((2, 5), np.int64, buf, 0)
+    cnt = np.ndarray((2,), np.int32, buf, 80)
+    assert ptr(idx) == ptr(buf) and ptr(cnt) == ptr(buf) + 80
+    with pytest.raises(ValueError):
+        ptr(a[:, ::2])
+    assert ptr(None) is None and ptr(1234) == 1234
+    with pytest.raises(TypeError):
+        ptr("nope")
