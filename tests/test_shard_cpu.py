@@ -1,5 +1,5 @@
 """N>1 path on CPU: world_size-2 gloo run of ShardedMatcher's partition / pack /
-all-gather / merge plumbing.  The two CUDA pieces (local match, merge) are injected
+all-gather / merge plumbing, plain steps and the two-slot pipeline (submit / result).  The two CUDA pieces (local match, merge) are injected
 with oracle-based stand-ins here; the real kernels are covered by the -m gpu tests."""
 import os
 import socket
@@ -68,6 +68,28 @@ def _worker(rank, world, port, q):
         ok = ok and int(anyst[0]) == 0
         for b in range(B):
             ok = ok and np.allclose(os_.numpy()[b, :wc[b]], ws[b, :wc[b]], atol=1e-6)
+        # two-slot pipeline (submit / result): two steps in flight give the answers of two plain
+        # steps, a third submit before a result is refused, tickets are checked
+        Q2 = np.ascontiguousarray(Q[::-1])
+        t0 = m.submit(torch.from_numpy(Q), tau, k, metric=1)
+        t1 = m.submit(torch.from_numpy(Q2), tau, k, metric=1)
+        try:
+            m.submit(torch.from_numpy(Q), tau, k, metric=1)
+            ok = False
+        except RuntimeError:
+            pass
+        r0 = [x.clone() for x in m.result(t0)]
+        r1 = [x.clone() for x in m.result(t1)]
+        try:
+            m.result(t0)
+            ok = False
+        except RuntimeError:
+            pass
+        w2 = o.cos_match_topk(G, Q2, tau, k, True)
+        ok = ok and np.array_equal(r0[0].numpy(), wi) and np.array_equal(r0[2].numpy(), wc.astype(np.int32))
+        ok = ok and np.array_equal(r1[0].numpy(), w2[0]) and np.array_equal(r1[2].numpy(), w2[2].astype(np.int32))
+        t2 = m.submit(torch.from_numpy(Q), tau, k, metric=1)       # slot 0 again
+        ok = ok and t2 == 2 and np.array_equal(m.wait_host(t2)[0].numpy(), wi)
         # every rank holds the same global answer
         gathered = [torch.zeros_like(oi) for _ in range(world)]
         dist.all_gather(gathered, oi)
