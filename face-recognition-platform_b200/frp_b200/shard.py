@@ -267,6 +267,9 @@ class ShardedMatcher:
             else:
                 recv = send
             self._merge(m, self.world, B, k, recv, out_idx, out_score, out_count, any_status, 0)
+            if host_out is not None:
+                for dst, src in zip(host_out, (out_idx, out_score, out_count, any_status)):
+                    dst.copy_(src)
         p["inflight"][slot] = (ticket, out_idx, out_score, out_count, any_status)
         p["n"] += 1
         return ticket
@@ -371,11 +374,13 @@ class CertifiedPipeline:
         t = matcher.torch
         self.m, self.B, self.k, self.device, self.depth = matcher, B, k, device, depth
         self.slots = []
+        self._cuda = t.device(device).type == "cuda"
+        pin = (lambda x: x.pin_memory()) if self._cuda else (lambda x: x)      # CPU tensors: the gloo tests
         for _ in range(depth):
             self.slots.append({
                 "q": t.empty((B, dim), dtype=t.float32, device=device),
-                "host": (t.empty((B, k), dtype=t.int64).pin_memory(), t.empty((B, k), dtype=t.float32).pin_memory(),
-                         t.empty((B,), dtype=t.int32).pin_memory(), t.zeros((1,), dtype=t.int32).pin_memory()),
+                "host": (pin(t.empty((B, k), dtype=t.int64)), pin(t.empty((B, k), dtype=t.float32)),
+                         pin(t.empty((B,), dtype=t.int32)), pin(t.zeros((1,), dtype=t.int32))),
                 "tau": None, "flags": 0, "ticket": None,
             })
         self.n = 0
@@ -399,7 +404,8 @@ class CertifiedPipeline:
             # rare: repeat this step through the ladder (synchronous), then copy again
             oi, os_, oc, level = self.m._ladder(s["q"], s["tau"], self.k, s["flags"], None)
             idx.copy_(oi); score.copy_(os_); count.copy_(oc)
-            t.cuda.current_stream(self.device).synchronize()
+            if self._cuda:
+                t.cuda.current_stream(self.device).synchronize()
         return idx, score, count, level
 
     def flush(self):

@@ -161,3 +161,49 @@ def test_match_certified_walks_the_fallback_ladder():
     assert level == 2 and seen[2] == MATCH_NO_THRESHOLD | MATCH_FORCE_EXACT | MATCH_WIDE and len(seen) == 3
     level, seen = run(3)
     assert level == 3 and len(seen) == 3
+
+
+def test_certified_pipeline_defers_the_flag_check_and_repairs_flagged_steps():
+    """CertifiedPipeline on CPU tensors (single rank, injected stand-ins): push returns the
+    PREVIOUS step's result, the host copies carry the merged answer, a step whose certificate
+    flag is set is repeated through the ladder before it is handed out (level > 0), and flush
+    drains the last step."""
+    for p in (os.path.join(ROOT, "face-recognition-platform_b200"),):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    from frp_b200._capi import MATCH_FORCE_EXACT
+    from frp_b200.shard import CertifiedPipeline, ShardedMatcher, unpack_records
+    calls = []
+
+    def local_match(q_dev, B, tau, k, flags, idx, score, count, status, stream):
+        # "answer" = the first query component as row id; step 2 (marker 20) is uncertified
+        # until it is repeated against the exact master
+        marker = int(q_dev[0, 0])
+        calls.append((marker, flags))
+        idx.fill_(marker)
+        score.fill_(0.25)
+        count.fill_(1)
+        status.fill_(1 if (marker == 20 and not (flags & MATCH_FORCE_EXACT)) else 0)
+
+    def merge(metric, R, B, k, records, out_idx, out_score, out_count, any_status, stream):
+        idx, sc, cnt, st = unpack_records(records.numpy(), R, B, k)
+        out_idx.copy_(torch.from_numpy(idx[0]))
+        out_score.copy_(torch.from_numpy(sc[0]))
+        out_count.copy_(torch.from_numpy(cnt[0]))
+        any_status.fill_(int(st.max()))
+
+    import types
+    m = ShardedMatcher(types.SimpleNamespace(metric=1), 100, 0, 1, local_match=local_match, merge=merge,
+                       set_base=False)
+    pipe = CertifiedPipeline(m, 4, 8, 2, torch.device("cpu"))
+    outs = []
+    for marker in (10, 20, 30):
+        r = pipe.push(torch.full((4, 8), float(marker)), 0.3)
+        outs.append(None if r is None else (int(r[0][0, 0]), int(r[2][0]), r[3]))
+    last = pipe.flush()
+    outs.append((int(last[0][0, 0]), int(last[2][0]), last[3]))
+    assert pipe.flush() is None
+    assert outs == [None, (10, 1, 0), (20, 1, 1), (30, 1, 0)]
+    # the flagged step ran twice: once in the pipeline, once with FORCE_EXACT
+    assert [c for c in calls if c[0] == 20] == [(20, 0), (20, MATCH_FORCE_EXACT)]
